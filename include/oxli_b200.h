@@ -1,0 +1,192 @@
+/*
+ * oxli_b200.h -- C ABI of the B200-native k-mer counting engine.
+ *
+ * This is the drop-in boundary for the hot path of oxli-bio/oxli
+ * (reference: src/lib.rs, one pyo3 class `KmerCountTable`).  Every entry
+ * point replaces the Rust/sourmash code behind one group of reference
+ * methods; the reference lines each one stands in for are cited below
+ * (paths relative to the reference root).  A pyo3 crate would bind these
+ * with a plain `extern "C"` block; in this repository
+ * the host mirror is oxli_b200/csrc/pyoxli.cpp.
+ *
+ * Conventions
+ *   - plain C types only; all sizes are uint64_t; no exceptions cross the ABI.
+ *   - every function returns an oxg_status (0 = OK).  oxg_last_error() gives a
+ *     thread-local human-readable message for the last non-OK status.
+ *   - `oxg_table*` is an opaque handle to a count table living in the HBM of one
+ *     GPU.  One handle is used by one caller thread at a time (mirrors the
+ *     `&mut self` borrow of the reference, src/lib.rs:41-838).
+ *   - pointers named `d_*` are DEVICE pointers on the table's GPU; all other
+ *     pointers are HOST pointers (pageable or pinned; pinned avoids a staging
+ *     copy, see oxg_pinned_alloc).
+ *   - there is no CPU fallback: every call fails with OXG_ERR_CUDA when no
+ *     usable sm_100 device is present.
+ */
+#ifndef OXLI_B200_H
+#define OXLI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum oxg_status {
+    OXG_OK = 0,
+    OXG_ERR_CUDA = 1,        /* CUDA runtime failure / no device */
+    OXG_ERR_INVALID = 2,     /* bad argument */
+    OXG_ERR_BAD_KMER = 3,    /* non-ACGT window met in error mode (src/lib.rs:593-596) */
+    OXG_ERR_NOMEM = 4,       /* host or device allocation failed */
+    OXG_ERR_WRONG_KSIZE = 5, /* k-mer length != table ksize (src/lib.rs:66-67,146-149) */
+    OXG_ERR_TOO_SMALL = 6    /* caller-provided output buffer too small */
+} oxg_status;
+
+typedef struct oxg_table oxg_table;
+
+/* thread-local message for the last failing call on this thread */
+const char *oxg_last_error(void);
+/* library version string; `KmerCountTable.version` (src/lib.rs:27,525-527) */
+const char *oxg_version(void);
+/* number of visible CUDA devices (0 when none; never fails) */
+int oxg_device_count(void);
+
+/* ---- lifecycle: KmerCountTable::new (src/lib.rs:44-62) -------------------
+ * ksize in 1..255.  capacity_hint = expected number of distinct k-mers (0 =
+ * unknown; the table grows by rehashing on the device). */
+oxg_status oxg_table_create(int device, uint32_t ksize, uint64_t capacity_hint, oxg_table **out);
+oxg_status oxg_table_destroy(oxg_table *t);
+/* drop every entry, keep the allocation */
+oxg_status oxg_table_clear(oxg_table *t);
+/* make room for `n_keys` distinct keys without further growth */
+oxg_status oxg_table_reserve(oxg_table *t, uint64_t n_keys);
+oxg_status oxg_table_ksize(const oxg_table *t, uint32_t *ksize);
+/* slots currently allocated (16 B each) */
+oxg_status oxg_table_capacity(const oxg_table *t, uint64_t *slots);
+
+/* ---- sequence -> hashes: sourmash SeqToHashes(force=true) as driven from
+ * src/lib.rs:65-81 (hash_kmer) and 873-881 (kmers_and_hashes) ---------------
+ * One hash per window of `seq` (len-k+1 entries, none when len < k); 0 marks a
+ * window holding a non-ACGT byte.  Runs the same device code as consume. */
+oxg_status oxg_hash_windows(oxg_table *t, const uint8_t *seq, uint64_t len, uint64_t *hashes_out);
+
+/* ---- bulk ingest: KmerCountTable::consume (src/lib.rs:545-607) ------------
+ * A batch is a flat byte buffer plus n_reads+1 offsets (CSR); read r is
+ * bases[offsets[r] .. offsets[r+1]).  Semantics are those of calling
+ * consume(read_r, skip_bad) for r = 0, 1, ... in order:
+ *   skip_bad != 0  windows holding a non-ACGT byte are skipped, not counted.
+ *   skip_bad == 0  reads before the first read with a bad window are counted in
+ *                  full; in that read the windows before the first bad one are
+ *                  counted and stay counted; nothing after it is.  The call
+ *                  then returns OXG_ERR_BAD_KMER with *err_read = that read and
+ *                  *err_pos = the number of its windows counted (the {n} of
+ *                  "bad k-mer encountered at position {n}").
+ * *total_counted = k-mers added to the table (valid windows whose hash is 0 are
+ * skipped and not counted, src/lib.rs:589).  err_read = -1 when no error.
+ * The host variant streams the buffer to the GPU in chunks with
+ * double-buffered cudaMemcpyAsync. */
+oxg_status oxg_consume_batch(oxg_table *t, const uint8_t *bases, const uint64_t *offsets,
+                             uint64_t n_reads, int skip_bad, uint64_t *total_counted,
+                             int64_t *err_read, uint64_t *err_pos);
+/* same, inputs already resident in the table's HBM */
+oxg_status oxg_consume_batch_device(oxg_table *t, const uint8_t *d_bases, const uint64_t *d_offsets,
+                                    uint64_t n_reads, uint64_t total_bases, int skip_bad,
+                                    uint64_t *total_counted, int64_t *err_read,
+                                    uint64_t *err_pos);
+/* ---- increment / lookup by hash (src/lib.rs:100-104, 185-194, 675-681) ---- */
+/* counts[h] += 1 for every h; new_counts (nullable) receives the count after
+ * each increment (exact for distinct hashes; for duplicates inside one call the
+ * values are the counts seen by each increment in some serial order). */
+oxg_status oxg_count_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, uint64_t *new_counts);
+oxg_status oxg_count_hashes_device(oxg_table *t, const uint64_t *d_hashes, uint64_t n);
+/* counts_out[i] = counts.get(hashes[i]).unwrap_or(0), order-preserving */
+oxg_status oxg_get_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, uint64_t *counts_out);
+/* counts.insert(h, v): overwrite or create (0 is a legal stored value) */
+oxg_status oxg_set_hash(oxg_table *t, uint64_t hash, uint64_t value);
+/* counts.remove(h) for each h (src/lib.rs:197-224); *n_removed nullable */
+oxg_status oxg_erase_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, uint64_t *n_removed);
+/* mincut (mode 0: remove count < thresh, src/lib.rs:227-246) / maxcut (mode 1:
+ * remove count > thresh, src/lib.rs:249-267) */
+oxg_status oxg_cut(oxg_table *t, int mode, uint64_t thresh, uint64_t *n_removed);
+
+/* ---- scans: __len__, sum_counts, min, max, histo (src/lib.rs:464-539,665) -- */
+typedef struct oxg_stats {
+    uint64_t len; /* distinct keys */
+    uint64_t sum; /* sum of counts (wrapping u64) */
+    uint64_t min; /* 0 when empty */
+    uint64_t max; /* 0 when empty */
+} oxg_stats;
+oxg_status oxg_table_len(oxg_table *t, uint64_t *len);
+oxg_status oxg_table_stats(oxg_table *t, oxg_stats *out);
+/* histo(zero=False): (freq, n) pairs sorted by freq.  Writes min(*n_out, cap)
+ * pairs; call with cap = 0 to size the buffers. */
+oxg_status oxg_histo(oxg_table *t, uint64_t *freq, uint64_t *n, uint64_t cap, uint64_t *n_out);
+
+/* ---- export: hashes / dump / __iter__ (src/lib.rs:330-381, 517-521, 658) ---
+ * sort_mode 0: table (slot) order -- stable between calls while the table is
+ * not modified, so dump() == list(iter); 1: by key; 2: by (count, key). */
+oxg_status oxg_export(oxg_table *t, uint64_t *keys, uint64_t *vals, uint64_t cap, int sort_mode,
+                      uint64_t *n_out);
+
+/* ---- set comparisons on key sets (src/lib.rs:610-655, 708-722) ------------ */
+oxg_status oxg_setop_sizes(oxg_table *a, oxg_table *b, uint64_t *inter, uint64_t *uni);
+typedef enum oxg_setop {
+    OXG_UNION = 0,
+    OXG_INTERSECTION = 1,
+    OXG_DIFFERENCE = 2,
+    OXG_SYMMETRIC_DIFFERENCE = 3
+} oxg_setop;
+/* writes min(*n_out, cap) keys (unordered) */
+oxg_status oxg_setop_export(oxg_table *a, oxg_table *b, int op, uint64_t *keys_out, uint64_t cap,
+                            uint64_t *n_out);
+/* n(A&B) / n(A|B) as one IEEE-754 double divide; 1.0 when both are empty */
+oxg_status oxg_jaccard(oxg_table *a, oxg_table *b, double *out);
+/* cosine similarity of the count vectors (src/lib.rs:727-765) */
+oxg_status oxg_cosine(oxg_table *a, oxg_table *b, double *out);
+
+/* ---- merge: KmerCountTable::add (src/lib.rs:778-837) ---------------------- */
+oxg_status oxg_merge(oxg_table *dst, oxg_table *src, uint64_t *counts_added, uint64_t *new_keys);
+
+/* ---- multi-GPU building blocks (table sharded by the high bits of the hash;
+ * one process per GPU, the exchange itself is done by the caller: NCCL
+ * all-to-all or peer stores) ------------------------------------------------
+ * Hash a device-resident batch; hashes owned by `self_rank` (owner(h) =
+ * h >> (64 - log2 n_ranks)) are counted into `t` directly, the others are
+ * appended to d_out[owner] (capacity out_cap entries each).  d_out_counts
+ * (n_ranks entries, device) receives the number appended per destination;
+ * counts are also copied to out_counts (host).  n_ranks must be a power of two
+ * <= 64. */
+oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const uint64_t *d_offsets,
+                                  uint64_t n_reads, uint64_t total_bases, int n_ranks,
+                                  int self_rank, uint64_t *const *d_out, uint64_t out_cap,
+                                  uint64_t *d_out_counts, uint64_t *out_counts,
+                                  uint64_t *local_counted);
+
+/* ---- synthetic reads for benchmarks ----------------
+ * Fills d_bases with n_reads reads of read_len bases drawn from a random genome
+ * of genome_len bases (counter-based splitmix64; strand flip with p=1/2;
+ * substitutions with probability sub_ppm/1e6, N with probability n_ppm/1e6).
+ * Read i is a pure function of (seed, first_read + i). */
+oxg_status oxg_synth_reads_device(int device, uint8_t *d_bases, uint64_t n_reads, uint32_t read_len,
+                                  uint64_t genome_len, uint64_t seed, uint64_t first_read,
+                                  uint32_t sub_ppm, uint32_t n_ppm);
+
+/* ---- host helpers ---------------------------------------------------------- */
+oxg_status oxg_pinned_alloc(uint64_t bytes, void **out);
+oxg_status oxg_pinned_free(void *p);
+oxg_status oxg_device_alloc(int device, uint64_t bytes, void **d_out);
+oxg_status oxg_device_free(int device, void *d_ptr);
+oxg_status oxg_memcpy_h2d(int device, void *d_dst, const void *src, uint64_t bytes);
+oxg_status oxg_memcpy_d2h(int device, void *dst, const void *d_src, uint64_t bytes);
+/* block until everything queued for this table's GPU has finished */
+oxg_status oxg_sync(oxg_table *t);
+/* kernels launched by this library in this process so far (bench bookkeeping) */
+uint64_t oxg_launch_count(void);
+/* device-time of the consume kernels of the last oxg_consume_* call on `t`, in
+ * milliseconds, and their number (CUDA events on the launch stream) */
+oxg_status oxg_last_consume_kernel_ms(oxg_table *t, float *ms, uint64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OXLI_B200_H */

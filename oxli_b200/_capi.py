@@ -1,0 +1,320 @@
+"""ctypes declarations for the C ABI in include/oxli_b200.h.
+
+Thin, typed access to `liboxli_b200.so` for bench.py, the sharded driver and
+the low-level tests (device-pointer entry points).  The drop-in
+`KmerCountTable` class is the compiled module `oxli_b200._oxli`
+(csrc/pyoxli.cpp); both sit on the same C ABI.  There is no fallback: a missing
+library raises ImportError, a missing GPU makes every call raise OxliCudaError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboxli_b200.so")
+
+OK, ERR_CUDA, ERR_INVALID, ERR_BAD_KMER, ERR_NOMEM, ERR_WRONG_KSIZE, ERR_TOO_SMALL = range(7)
+
+u64 = C.c_uint64
+u64p = C.POINTER(C.c_uint64)
+vp = C.c_void_p
+
+
+class OxliError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(msg)
+        self.status = status
+
+
+class OxliCudaError(OxliError):
+    pass
+
+
+class oxg_stats(C.Structure):
+    _fields_ = [("len", u64), ("sum", u64), ("min", u64), ("max", u64)]
+
+
+# name -> (restype, argtypes).  Must list every symbol the header declares
+# (tests/test_abi.py parses the header and checks).
+SIGNATURES = {
+    "oxg_last_error": (C.c_char_p, []),
+    "oxg_version": (C.c_char_p, []),
+    "oxg_device_count": (C.c_int, []),
+    "oxg_table_create": (C.c_int, [C.c_int, C.c_uint32, u64, C.POINTER(vp)]),
+    "oxg_table_destroy": (C.c_int, [vp]),
+    "oxg_table_clear": (C.c_int, [vp]),
+    "oxg_table_reserve": (C.c_int, [vp, u64]),
+    "oxg_table_ksize": (C.c_int, [vp, C.POINTER(C.c_uint32)]),
+    "oxg_table_capacity": (C.c_int, [vp, u64p]),
+    "oxg_hash_windows": (C.c_int, [vp, vp, u64, vp]),
+    "oxg_consume_batch": (C.c_int, [vp, vp, vp, u64, C.c_int, u64p, C.POINTER(C.c_int64), u64p]),
+    "oxg_consume_batch_device": (C.c_int, [vp, vp, vp, u64, u64, C.c_int, u64p, C.POINTER(C.c_int64), u64p]),
+    "oxg_count_hashes": (C.c_int, [vp, vp, u64, vp]),
+    "oxg_count_hashes_device": (C.c_int, [vp, vp, u64]),
+    "oxg_get_hashes": (C.c_int, [vp, vp, u64, vp]),
+    "oxg_set_hash": (C.c_int, [vp, u64, u64]),
+    "oxg_erase_hashes": (C.c_int, [vp, vp, u64, u64p]),
+    "oxg_cut": (C.c_int, [vp, C.c_int, u64, u64p]),
+    "oxg_table_len": (C.c_int, [vp, u64p]),
+    "oxg_table_stats": (C.c_int, [vp, C.POINTER(oxg_stats)]),
+    "oxg_histo": (C.c_int, [vp, vp, vp, u64, u64p]),
+    "oxg_export": (C.c_int, [vp, vp, vp, u64, C.c_int, u64p]),
+    "oxg_setop_sizes": (C.c_int, [vp, vp, u64p, u64p]),
+    "oxg_setop_export": (C.c_int, [vp, vp, C.c_int, vp, u64, u64p]),
+    "oxg_jaccard": (C.c_int, [vp, vp, C.POINTER(C.c_double)]),
+    "oxg_cosine": (C.c_int, [vp, vp, C.POINTER(C.c_double)]),
+    "oxg_merge": (C.c_int, [vp, vp, u64p, u64p]),
+    "oxg_route_batch_device": (C.c_int, [vp, vp, vp, u64, u64, C.c_int, C.c_int, C.POINTER(vp), u64, vp, vp, u64p]),
+    "oxg_synth_reads_device": (C.c_int, [C.c_int, vp, u64, C.c_uint32, u64, u64, u64, C.c_uint32, C.c_uint32]),
+    "oxg_pinned_alloc": (C.c_int, [u64, C.POINTER(vp)]),
+    "oxg_pinned_free": (C.c_int, [vp]),
+    "oxg_device_alloc": (C.c_int, [C.c_int, u64, C.POINTER(vp)]),
+    "oxg_device_free": (C.c_int, [C.c_int, vp]),
+    "oxg_memcpy_h2d": (C.c_int, [C.c_int, vp, vp, u64]),
+    "oxg_memcpy_d2h": (C.c_int, [C.c_int, vp, vp, u64]),
+    "oxg_sync": (C.c_int, [vp]),
+    "oxg_launch_count": (u64, []),
+    "oxg_last_consume_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float), u64p]),
+}
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m oxli_b200._build` "
+            "(nvcc, sm_100a). oxli_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int) -> None:
+    if status == OK:
+        return
+    msg = (lib.oxg_last_error() or b"").decode(errors="replace")
+    if status == ERR_CUDA:
+        raise OxliCudaError(status, msg)
+    raise OxliError(status, msg)
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data
+
+
+class Table:
+    """Low-level handle wrapper (numpy in/out).  Not the drop-in class."""
+
+    def __init__(self, ksize: int, device: int = 0, capacity_hint: int = 0):
+        self._h = vp()
+        check(lib.oxg_table_create(device, ksize, capacity_hint, C.byref(self._h)))
+        self.ksize = ksize
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.oxg_table_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def clear(self):
+        check(lib.oxg_table_clear(self._h))
+
+    def reserve(self, n):
+        check(lib.oxg_table_reserve(self._h, n))
+
+    @property
+    def capacity(self) -> int:
+        v = u64()
+        check(lib.oxg_table_capacity(self._h, C.byref(v)))
+        return int(v.value)
+
+    def hash_windows(self, seq: bytes | np.ndarray) -> np.ndarray:
+        a = np.frombuffer(seq, dtype=np.uint8) if not isinstance(seq, np.ndarray) else np.ascontiguousarray(seq, dtype=np.uint8)
+        n = max(len(a) - self.ksize + 1, 0)
+        out = np.zeros(n, dtype=np.uint64)
+        if n:
+            check(lib.oxg_hash_windows(self._h, a.ctypes.data, len(a), out.ctypes.data))
+        return out
+
+    def consume_batch(self, bases: np.ndarray, offsets: np.ndarray, skip_bad: bool = True):
+        """Returns (status, total_counted, err_read, err_pos); status is OK or ERR_BAD_KMER."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        total, er, ep = u64(), C.c_int64(), u64()
+        st = lib.oxg_consume_batch(self._h, _ptr(bases), _ptr(offsets), len(offsets) - 1, 1 if skip_bad else 0,
+                                   C.byref(total), C.byref(er), C.byref(ep))
+        if st not in (OK, ERR_BAD_KMER):
+            check(st)
+        return st, int(total.value), int(er.value), int(ep.value)
+
+    def consume_batch_device(self, d_bases: int, d_offsets: int, n_reads: int, total_bases: int, skip_bad: bool = True):
+        total, er, ep = u64(), C.c_int64(), u64()
+        st = lib.oxg_consume_batch_device(self._h, d_bases, d_offsets, n_reads, total_bases, 1 if skip_bad else 0,
+                                          C.byref(total), C.byref(er), C.byref(ep))
+        if st not in (OK, ERR_BAD_KMER):
+            check(st)
+        return st, int(total.value), int(er.value), int(ep.value)
+
+    def count_hashes(self, hashes, want_counts: bool = False):
+        h = np.ascontiguousarray(hashes, dtype=np.uint64)
+        out = np.empty(len(h), dtype=np.uint64) if want_counts else None
+        check(lib.oxg_count_hashes(self._h, _ptr(h), len(h), _ptr(out)))
+        return out
+
+    def count_hashes_device(self, d_hashes: int, n: int):
+        check(lib.oxg_count_hashes_device(self._h, d_hashes, n))
+
+    def get_hashes(self, hashes) -> np.ndarray:
+        h = np.ascontiguousarray(hashes, dtype=np.uint64)
+        out = np.zeros(len(h), dtype=np.uint64)
+        check(lib.oxg_get_hashes(self._h, _ptr(h), len(h), _ptr(out)))
+        return out
+
+    def set_hash(self, h: int, v: int):
+        check(lib.oxg_set_hash(self._h, h, v))
+
+    def erase_hashes(self, hashes) -> int:
+        h = np.ascontiguousarray(hashes, dtype=np.uint64)
+        n = u64()
+        check(lib.oxg_erase_hashes(self._h, _ptr(h), len(h), C.byref(n)))
+        return int(n.value)
+
+    def cut(self, mode: int, thresh: int) -> int:
+        n = u64()
+        check(lib.oxg_cut(self._h, mode, thresh, C.byref(n)))
+        return int(n.value)
+
+    def __len__(self) -> int:
+        n = u64()
+        check(lib.oxg_table_len(self._h, C.byref(n)))
+        return int(n.value)
+
+    def stats(self) -> dict:
+        s = oxg_stats()
+        check(lib.oxg_table_stats(self._h, C.byref(s)))
+        return {"len": int(s.len), "sum": int(s.sum), "min": int(s.min), "max": int(s.max)}
+
+    def histo(self) -> list[tuple[int, int]]:
+        n = u64()
+        check(lib.oxg_histo(self._h, None, None, 0, C.byref(n)))
+        f = np.zeros(max(int(n.value), 1), dtype=np.uint64)
+        c = np.zeros(max(int(n.value), 1), dtype=np.uint64)
+        check(lib.oxg_histo(self._h, _ptr(f), _ptr(c), len(f), C.byref(n)))
+        return [(int(f[i]), int(c[i])) for i in range(int(n.value))]
+
+    def export(self, sort_mode: int = 0) -> tuple[np.ndarray, np.ndarray]:
+        n = u64()
+        check(lib.oxg_export(self._h, None, None, 0, sort_mode, C.byref(n)))
+        m = int(n.value)
+        k = np.zeros(max(m, 1), dtype=np.uint64)
+        v = np.zeros(max(m, 1), dtype=np.uint64)
+        if m:
+            check(lib.oxg_export(self._h, _ptr(k), _ptr(v), m, sort_mode, C.byref(n)))
+        return k[:m], v[:m]
+
+    def setop_sizes(self, other: "Table") -> tuple[int, int]:
+        i, u = u64(), u64()
+        check(lib.oxg_setop_sizes(self._h, other._h, C.byref(i), C.byref(u)))
+        return int(i.value), int(u.value)
+
+    def setop(self, other: "Table", op: int) -> np.ndarray:
+        cap = len(self) + len(other) + 2
+        out = np.zeros(cap, dtype=np.uint64)
+        n = u64()
+        check(lib.oxg_setop_export(self._h, other._h, op, _ptr(out), cap, C.byref(n)))
+        return out[: int(n.value)]
+
+    def jaccard(self, other: "Table") -> float:
+        d = C.c_double()
+        check(lib.oxg_jaccard(self._h, other._h, C.byref(d)))
+        return float(d.value)
+
+    def cosine(self, other: "Table") -> float:
+        d = C.c_double()
+        check(lib.oxg_cosine(self._h, other._h, C.byref(d)))
+        return float(d.value)
+
+    def merge(self, other: "Table") -> tuple[int, int]:
+        a, n = u64(), u64()
+        check(lib.oxg_merge(self._h, other._h, C.byref(a), C.byref(n)))
+        return int(a.value), int(n.value)
+
+    def sync(self):
+        check(lib.oxg_sync(self._h))
+
+    def last_consume_kernel_ms(self) -> tuple[float, int]:
+        ms, n = C.c_float(), u64()
+        check(lib.oxg_last_consume_kernel_ms(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def digest(self) -> dict:
+        """Order-independent digests of the (hash, count) multiset (test helper)."""
+        k, v = self.export(1)
+        with np.errstate(over="ignore"):
+            return {
+                "n": int(len(k)),
+                "sum": int(v.sum(dtype=np.uint64)),
+                "xor": int(np.bitwise_xor.reduce(k)) if len(k) else 0,
+                "sum_hc": int((k * v).sum(dtype=np.uint64)),
+            }
+
+
+def device_alloc(nbytes: int, device: int = 0) -> int:
+    p = vp()
+    check(lib.oxg_device_alloc(device, nbytes, C.byref(p)))
+    return int(p.value)
+
+
+def device_free(ptr: int, device: int = 0) -> None:
+    check(lib.oxg_device_free(device, ptr))
+
+
+def h2d(d_dst: int, src: np.ndarray, device: int = 0) -> None:
+    src = np.ascontiguousarray(src)
+    check(lib.oxg_memcpy_h2d(device, d_dst, src.ctypes.data, src.nbytes))
+
+
+def d2h(dst: np.ndarray, d_src: int, device: int = 0) -> None:
+    check(lib.oxg_memcpy_d2h(device, dst.ctypes.data, d_src, dst.nbytes))
+
+
+def synth_reads_device(d_bases: int, n_reads: int, read_len: int, genome_len: int, seed: int,
+                       first_read: int = 0, sub_ppm: int = 0, n_ppm: int = 0, device: int = 0) -> None:
+    check(lib.oxg_synth_reads_device(device, d_bases, n_reads, read_len, genome_len, seed, first_read, sub_ppm, n_ppm))
+
+
+def pinned_empty(nbytes: int) -> np.ndarray:
+    """uint8 numpy view of freshly allocated pinned host memory (freed with the array)."""
+    p = vp()
+    check(lib.oxg_pinned_alloc(nbytes, C.byref(p)))
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8, count=nbytes)
+    _PINNED[arr.ctypes.data] = p.value
+    return arr
+
+
+_PINNED: dict[int, int] = {}
+
+
+def pinned_free(arr: np.ndarray) -> None:
+    p = _PINNED.pop(arr.ctypes.data, None)
+    if p:
+        lib.oxg_pinned_free(p)

@@ -1,0 +1,1125 @@
+// capi.cu -- host side of the C ABI declared in include/oxli_b200.h.
+//
+// One DeviceCtx per GPU (streams, staging buffers, scratch), one oxg_table per
+// count table.  Everything is plain CUDA runtime: no torch, no Thrust/CUB.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstddef>
+#include <future>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/oxli_b200.h"
+#include "consume.cuh"
+#include "tableops.cuh"
+
+using namespace oxg;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+oxg_status fail(oxg_status st, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return st;
+}
+
+#define CU(expr)                                                                             \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(e__ == cudaErrorMemoryAllocation ? OXG_ERR_NOMEM : OXG_ERR_CUDA,     \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__,   \
+                        __LINE__);                                                           \
+    } while (0)
+#define TRY(expr)                          \
+    do {                                   \
+        oxg_status s__ = (expr);           \
+        if (s__ != OXG_OK) return s__;     \
+    } while (0)
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+constexpr uint64_t kChunkBytes = 64ull << 20;     // host->device streaming granule
+constexpr uint64_t kLaunchWindows = 64ull << 20;  // windows per consume launch (bounds the overflow list)
+constexpr uint64_t kSmallBatch = 1ull << 20;      // below this, reserve for the worst case up front
+constexpr uint64_t kMinCap = 1024;
+
+struct DeviceCtx {
+    int dev = -1;
+    int sms = 0;
+    cudaStream_t stream = nullptr, copy = nullptr;
+    std::mutex mu;
+    // double-buffered staging for host batches
+    uint8_t *d_stage[2] = {nullptr, nullptr};
+    uint8_t *h_stage[2] = {nullptr, nullptr};
+    uint64_t *d_offs[2] = {nullptr, nullptr};
+    uint64_t *h_offs[2] = {nullptr, nullptr};
+    uint64_t offs_cap[2] = {0, 0};
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    // scratch
+    uint64_t *d_tile_first = nullptr; uint64_t tile_first_cap = 0;
+    uint64_t *d_overflow = nullptr;   uint64_t overflow_cap = 0;
+    uint64_t *d_dense = nullptr;      // kHistDense bins
+    uint64_t *d_big = nullptr;        uint64_t big_cap = 0;
+    uint64_t *d_io = nullptr;         uint64_t io_cap = 0;   // generic u64 in/out scratch (device)
+    uint64_t *h_io = nullptr;         uint64_t h_io_cap = 0; // pinned mirror
+    double *d_f64 = nullptr;          // 4 doubles
+};
+
+std::mutex g_ctx_mu;
+std::vector<std::unique_ptr<DeviceCtx>> g_ctx;
+
+oxg_status get_ctx(int dev, DeviceCtx **out) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(OXG_ERR_CUDA, "no CUDA device available (oxli_b200 has no CPU fallback)");
+    }
+    if (dev < 0 || dev >= n) return fail(OXG_ERR_INVALID, "device %d out of range (have %d)", dev, n);
+    if ((int)g_ctx.size() < n) g_ctx.resize(n);
+    if (!g_ctx[dev]) {
+        auto c = std::make_unique<DeviceCtx>();
+        c->dev = dev;
+        CU(cudaSetDevice(dev));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major < 10)
+            return fail(OXG_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                        dev, prop.major, prop.minor);
+        c->sms = prop.multiProcessorCount;
+        CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+        }
+        CU(cudaEventCreate(&c->ev_t0));
+        CU(cudaEventCreate(&c->ev_t1));
+        CU(cudaMalloc(&c->d_dense, kHistDense * sizeof(uint64_t)));
+        CU(cudaMalloc(&c->d_f64, 4 * sizeof(double)));
+        g_ctx[dev] = std::move(c);
+    }
+    *out = g_ctx[dev].get();
+    return OXG_OK;
+}
+
+template <class T>
+oxg_status ensure_dev(T **p, uint64_t *cap, uint64_t want) {
+    if (*cap >= want && *p) return OXG_OK;
+    if (*p) CU(cudaFree(*p));
+    *p = nullptr; *cap = 0;
+    uint64_t ncap = std::max<uint64_t>(want, 1024);
+    CU(cudaMalloc(p, ncap * sizeof(T)));
+    *cap = ncap;
+    return OXG_OK;
+}
+
+oxg_status ensure_io(DeviceCtx *c, uint64_t n) {
+    TRY(ensure_dev(&c->d_io, &c->io_cap, n));
+    if (c->h_io_cap < n) {
+        if (c->h_io) CU(cudaFreeHost(c->h_io));
+        c->h_io = nullptr; c->h_io_cap = 0;
+        uint64_t ncap = std::max<uint64_t>(n, 1024);
+        CU(cudaMallocHost(&c->h_io, ncap * sizeof(uint64_t)));
+        c->h_io_cap = ncap;
+    }
+    return OXG_OK;
+}
+
+int grid_for(const DeviceCtx *c, uint64_t items, int threads, int per_sm) {
+    uint64_t want = (items + threads - 1) / threads;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->sms * per_sm));
+}
+
+uint64_t pow2_at_least(uint64_t x) {
+    uint64_t c = kMinCap;
+    while (c < x) c <<= 1;
+    return c;
+}
+
+}  // namespace
+
+struct oxg_table {
+    DeviceCtx *ctx = nullptr;
+    uint32_t k = 0;
+    ulonglong2 *slots = nullptr;
+    uint64_t cap = 0;
+    Ctrl *d_ctrl = nullptr;
+    Ctrl *h_ctrl = nullptr;  // pinned
+    uint64_t size = 0;       // host mirror of ctrl->size as of the last sync
+    float last_ms = 0.f;
+    uint64_t last_launches = 0;
+};
+
+namespace {
+
+TableView view_of(const oxg_table *t, bool with_overflow) {
+    TableView v;
+    v.slots = t->slots;
+    v.cap = t->cap;
+    uint32_t lg = 0;
+    while ((1ull << lg) < t->cap) ++lg;
+    v.shift = 64 - lg;
+    v.limit = t->cap - t->cap / 4;  // stop creating keys at 75 % load
+    v.ctrl = t->d_ctrl;
+    v.overflow = with_overflow ? t->ctx->d_overflow : nullptr;
+    v.overflow_cap = with_overflow ? t->ctx->overflow_cap : 0;
+    return v;
+}
+
+oxg_status pull_ctrl(oxg_table *t) {
+    DeviceCtx *c = t->ctx;
+    CU(cudaMemcpyAsync(t->h_ctrl, t->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    t->size = t->h_ctrl->size;
+    return OXG_OK;
+}
+
+// zero the ctrl fields [first, first+n) (in uint64 units)
+oxg_status zero_ctrl_fields(oxg_table *t, size_t first_field, size_t n_fields) {
+    CU(cudaMemsetAsync(reinterpret_cast<uint64_t *>(t->d_ctrl) + first_field, 0, n_fields * 8, t->ctx->stream));
+    return OXG_OK;
+}
+constexpr size_t kFieldCounted = offsetof(Ctrl, counted) / 8;
+constexpr size_t kFieldScratch = offsetof(Ctrl, scratch) / 8;
+
+oxg_status alloc_slots(DeviceCtx *c, uint64_t cap, ulonglong2 **out) {
+    CU(cudaMalloc(out, cap * sizeof(ulonglong2)));
+    init_slots_kernel<<<grid_for(c, cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(*out, cap);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return OXG_OK;
+}
+
+// grow (or rebuild at the same size) so that `keys` distinct keys sit at <= 50 % load
+oxg_status grow_to_fit(oxg_table *t, uint64_t keys) {
+    uint64_t want = pow2_at_least(keys * 2);
+    if (want <= t->cap) return OXG_OK;
+    DeviceCtx *c = t->ctx;
+    ulonglong2 *fresh = nullptr;
+    TRY(alloc_slots(c, want, &fresh));
+    ulonglong2 *old = t->slots;
+    const uint64_t old_cap = t->cap;
+    t->slots = fresh;
+    t->cap = want;
+    if (t->size) {
+        rehash_kernel<<<grid_for(c, old_cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(old, old_cap, view_of(t, false));
+        LAUNCHED();
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(old));
+    return OXG_OK;
+}
+
+oxg_status reserve_keys(oxg_table *t, uint64_t extra) { return grow_to_fit(t, t->size + extra); }
+
+template <int MODE>
+oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
+    DeviceCtx *c = t->ctx;
+    const int k = (int)t->k;
+    int grid = (int)std::min<uint64_t>(p.n_tiles, (uint64_t)c->sms * 8);
+    if (grid < 1) grid = 1;
+    switch (k) {
+#define OXG_CASE(KK)                                                                    \
+    case KK:                                                                            \
+        consume_kernel<KK, MODE><<<grid, kThreads, 0, c->stream>>>(p);                  \
+        break;
+        OXG_CASE(21)
+        OXG_CASE(31)
+#undef OXG_CASE
+    default:
+        if (MODE == kModeRoute) return fail(OXG_ERR_INVALID, "sharded routing is built for k = 21 and 31 only");
+        if constexpr (MODE != kModeRoute) {
+            const size_t smem = generic_smem_bytes(k);
+            consume_generic_kernel<MODE><<<grid, kThreads, smem, c->stream>>>(p);
+        }
+    }
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return OXG_OK;
+}
+
+// Run one mode over window starts [w_lo, w_hi) of a device-resident span.
+// `bases` holds global positions [g0, data_end); offsets are global positions.
+// kModeCount: loops launches of <= kLaunchWindows windows, growing the table and
+// replaying deferred hashes between launches.  *counted accumulates.
+oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0, uint64_t w_lo,
+                    uint64_t w_hi, uint64_t data_end, const uint64_t *d_offsets, uint64_t n_off,
+                    uint64_t *hashes_out, uint64_t *counted) {
+    DeviceCtx *c = t->ctx;
+    if (w_hi <= w_lo) return OXG_OK;
+    if ((reinterpret_cast<uintptr_t>(d_bases) & 15) || (g0 & 15))
+        return fail(OXG_ERR_INVALID, "device base buffer must be 16-byte aligned");
+    uint64_t lo = w_lo;
+    while (lo < w_hi) {
+        const uint64_t tile_base = std::max<uint64_t>(g0, lo & ~(uint64_t)15);
+        uint64_t hi = std::min<uint64_t>(w_hi, tile_base + kLaunchWindows);
+        const uint64_t n_tiles = (hi - tile_base + kTileW - 1) / kTileW;
+        TRY(ensure_dev(&c->d_tile_first, &c->tile_first_cap, n_tiles));
+        if (mode == kModeCount) {
+            const uint64_t span = hi - lo;
+            if (span <= kSmallBatch) TRY(reserve_keys(t, span));
+            else if (t->size * 2 > t->cap) TRY(grow_to_fit(t, t->size * 2));
+            TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, span));
+            TRY(zero_ctrl_fields(t, kFieldCounted, 2));  // counted, overflow
+        }
+        ConsumeParams p{};
+        p.bases = d_bases; p.g0 = g0; p.w_lo = lo; p.w_hi = hi; p.data_end = data_end;
+        p.tile_base = tile_base; p.n_tiles = n_tiles; p.offsets = d_offsets; p.n_off = n_off;
+        p.tile_first = c->d_tile_first; p.table = view_of(t, mode == kModeCount);
+        p.hashes_out = hashes_out ? hashes_out + (lo - w_lo) : nullptr; p.ksize = t->k;
+        tile_first_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(d_offsets, n_off, tile_base, n_tiles, c->d_tile_first);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->ev_t0, c->stream));
+        if (mode == kModeCount) TRY(launch_consume<kModeCount>(t, p));
+        else if (mode == kModeHash) TRY(launch_consume<kModeHash>(t, p));
+        else TRY(launch_consume<kModeFirstBad>(t, p));
+        CU(cudaEventRecord(c->ev_t1, c->stream));
+        if (mode == kModeCount) {
+            TRY(pull_ctrl(t));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+            t->last_ms += ms; t->last_launches += 1;
+            if (counted) *counted += t->h_ctrl->counted;
+            uint64_t ov = t->h_ctrl->overflow;
+            if (ov) {  // table hit its load limit: grow, then replay the deferred hashes
+                if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
+                TRY(grow_to_fit(t, t->size + ov));
+                count_hashes_kernel<<<grid_for(c, ov, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr);
+                LAUNCHED();
+                CU(cudaGetLastError());
+                TRY(pull_ctrl(t));
+            }
+        }
+        lo = hi;
+    }
+    return OXG_OK;
+}
+
+// error-mode driver on a device-resident batch (src/lib.rs:586-600 semantics)
+oxg_status consume_resident(oxg_table *t, const uint8_t *d_bases, const uint64_t *d_offsets,
+                            const uint64_t *h_offsets /*nullable*/, uint64_t n_reads,
+                            uint64_t total, int skip_bad, uint64_t *total_counted,
+                            int64_t *err_read, uint64_t *err_pos) {
+    DeviceCtx *c = t->ctx;
+    const uint64_t k = t->k;
+    uint64_t counted = 0;
+    if (err_read) *err_read = -1;
+    if (err_pos) *err_pos = 0;
+    t->last_ms = 0.f; t->last_launches = 0;
+    const uint64_t n_win = total >= k ? total - k + 1 : 0;
+    oxg_status ret = OXG_OK;
+    if (skip_bad || n_win == 0) {
+        TRY(run_span(t, kModeCount, d_bases, 0, 0, n_win, total, d_offsets, n_reads + 1, nullptr, &counted));
+    } else {
+        t->h_ctrl->first_bad = ~0ULL;
+        CU(cudaMemcpyAsync(&t->d_ctrl->first_bad, &t->h_ctrl->first_bad, 8, cudaMemcpyHostToDevice, c->stream));
+        TRY(run_span(t, kModeFirstBad, d_bases, 0, 0, n_win, total, d_offsets, n_reads + 1, nullptr, nullptr));
+        TRY(pull_ctrl(t));
+        const uint64_t fb = t->h_ctrl->first_bad;
+        if (fb == ~0ULL) {
+            TRY(run_span(t, kModeCount, d_bases, 0, 0, n_win, total, d_offsets, n_reads + 1, nullptr, &counted));
+        } else {
+            // read holding position fb: last r with offsets[r] <= fb
+            std::vector<uint64_t> tmp;
+            if (!h_offsets) {
+                tmp.resize(n_reads + 1);
+                CU(cudaMemcpyAsync(tmp.data(), d_offsets, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                h_offsets = tmp.data();
+            }
+            const uint64_t r = (uint64_t)(std::upper_bound(h_offsets, h_offsets + n_reads + 1, fb) - h_offsets) - 1;
+            const uint64_t r_start = h_offsets[r];
+            uint64_t in_read = 0;
+            // everything before that read, then the clean prefix of the read itself
+            TRY(run_span(t, kModeCount, d_bases, 0, 0, r_start >= k ? r_start - k + 1 : 0, r_start, d_offsets, n_reads + 1, nullptr, &counted));
+            TRY(run_span(t, kModeCount, d_bases, 0, r_start, fb, fb + k - 1, d_offsets, n_reads + 1, nullptr, &in_read));
+            counted += in_read;
+            if (err_read) *err_read = (int64_t)r;
+            if (err_pos) *err_pos = in_read;
+            ret = fail(OXG_ERR_BAD_KMER, "bad k-mer encountered at position %llu", (unsigned long long)in_read);
+        }
+    }
+    if (total_counted) *total_counted = counted;
+    return ret;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI ---
+
+extern "C" {
+
+const char *oxg_last_error(void) { return g_err.c_str(); }
+const char *oxg_version(void) { return "0.3.0"; }  // tracks the reference's Cargo.toml version
+int oxg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+uint64_t oxg_launch_count(void) { return g_launches.load(); }
+
+oxg_status oxg_table_create(int device, uint32_t ksize, uint64_t capacity_hint, oxg_table **out) {
+    if (!out) return fail(OXG_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (ksize < 1 || ksize > 255) return fail(OXG_ERR_INVALID, "ksize must be in 1..255 (got %u)", ksize);
+    DeviceCtx *c;
+    TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->dev));
+    auto t = std::make_unique<oxg_table>();
+    t->ctx = c; t->k = ksize;
+    t->cap = pow2_at_least(capacity_hint + capacity_hint / 2 + 1);  // <= 67 % load at the hint
+    CU(cudaMalloc(&t->d_ctrl, sizeof(Ctrl)));
+    CU(cudaMemsetAsync(t->d_ctrl, 0, sizeof(Ctrl), c->stream));
+    CU(cudaMallocHost(&t->h_ctrl, sizeof(Ctrl)));
+    memset(t->h_ctrl, 0, sizeof(Ctrl));
+    TRY(alloc_slots(c, t->cap, &t->slots));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = t.release();
+    return OXG_OK;
+}
+
+oxg_status oxg_table_destroy(oxg_table *t) {
+    if (!t) return OXG_OK;
+    std::lock_guard<std::mutex> lk(t->ctx->mu);
+    cudaSetDevice(t->ctx->dev);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->slots);
+    cudaFree(t->d_ctrl);
+    cudaFreeHost(t->h_ctrl);
+    delete t;
+    return OXG_OK;
+}
+
+#define ENTER(t)                                               \
+    if (!(t)) return fail(OXG_ERR_INVALID, "table is null");   \
+    DeviceCtx *c = (t)->ctx;                                   \
+    std::lock_guard<std::mutex> lk(c->mu);                     \
+    CU(cudaSetDevice(c->dev))
+
+oxg_status oxg_table_clear(oxg_table *t) {
+    ENTER(t);
+    init_slots_kernel<<<grid_for(c, t->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(t->slots, t->cap);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(t->d_ctrl, 0, sizeof(Ctrl), c->stream));
+    t->size = 0;
+    return OXG_OK;
+}
+
+oxg_status oxg_table_reserve(oxg_table *t, uint64_t n_keys) {
+    ENTER(t);
+    return grow_to_fit(t, std::max(n_keys, t->size));
+}
+
+oxg_status oxg_table_ksize(const oxg_table *t, uint32_t *ksize) {
+    if (!t || !ksize) return fail(OXG_ERR_INVALID, "null argument");
+    *ksize = t->k;
+    return OXG_OK;
+}
+
+oxg_status oxg_table_capacity(const oxg_table *t, uint64_t *slots) {
+    if (!t || !slots) return fail(OXG_ERR_INVALID, "null argument");
+    *slots = t->cap;
+    return OXG_OK;
+}
+
+oxg_status oxg_sync(oxg_table *t) {
+    ENTER(t);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy));
+    return OXG_OK;
+}
+
+oxg_status oxg_last_consume_kernel_ms(oxg_table *t, float *ms, uint64_t *launches) {
+    if (!t) return fail(OXG_ERR_INVALID, "table is null");
+    if (ms) *ms = t->last_ms;
+    if (launches) *launches = t->last_launches;
+    return OXG_OK;
+}
+
+// ---- hashing ---------------------------------------------------------------
+
+oxg_status oxg_hash_windows(oxg_table *t, const uint8_t *seq, uint64_t len, uint64_t *hashes_out) {
+    ENTER(t);
+    const uint64_t k = t->k;
+    if (len < k) return OXG_OK;
+    if (!seq || !hashes_out) return fail(OXG_ERR_INVALID, "null argument");
+    const uint64_t n_win = len - k + 1;
+    // piecewise so the device-side output stays bounded
+    const uint64_t piece = 4ull << 20;
+    uint8_t *d_seq = nullptr;
+    uint64_t *d_out = nullptr, *d_off = nullptr;
+    const uint64_t offs[2] = {0, len};
+    CU(cudaMalloc(&d_off, 16));
+    CU(cudaMemcpyAsync(d_off, offs, 16, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMalloc(&d_seq, std::min(len, piece + k - 1) + 16));
+    CU(cudaMalloc(&d_out, std::min(n_win, piece) * 8));
+    oxg_status st = OXG_OK;
+    for (uint64_t lo = 0; lo < n_win && st == OXG_OK; lo += piece) {
+        const uint64_t hi = std::min(n_win, lo + piece);
+        const uint64_t bytes = hi - lo + k - 1;
+        cudaMemcpyAsync(d_seq, seq + lo, bytes, cudaMemcpyHostToDevice, c->stream);
+        st = run_span(t, kModeHash, d_seq, lo, lo, hi, lo + bytes, d_off, 2, d_out, nullptr);
+        if (st != OXG_OK) break;
+        cudaMemcpyAsync(hashes_out + lo, d_out, (hi - lo) * 8, cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) st = fail(OXG_ERR_CUDA, "hash_windows: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaFree(d_seq); cudaFree(d_out); cudaFree(d_off);
+    return st;
+}
+
+// ---- consume ---------------------------------------------------------------
+
+oxg_status oxg_consume_batch_device(oxg_table *t, const uint8_t *d_bases, const uint64_t *d_offsets,
+                                    uint64_t n_reads, uint64_t total_bases, int skip_bad,
+                                    uint64_t *total_counted, int64_t *err_read, uint64_t *err_pos) {
+    ENTER(t);
+    if (total_counted) *total_counted = 0;
+    if (n_reads == 0 || total_bases == 0) { if (err_read) *err_read = -1; if (err_pos) *err_pos = 0; return OXG_OK; }
+    if (!d_bases || !d_offsets) return fail(OXG_ERR_INVALID, "null argument");
+    return consume_resident(t, d_bases, d_offsets, nullptr, n_reads, total_bases, skip_bad, total_counted, err_read, err_pos);
+}
+
+// Host batch: stream [w_lo, w_hi) through the two staging buffers.
+static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, const uint64_t *offsets,
+                              uint64_t n_reads, uint64_t w_lo, uint64_t w_hi, uint64_t data_end,
+                              bool src_pinned, uint64_t *counted) {
+    DeviceCtx *c = t->ctx;
+    const uint64_t k = t->k;
+    if (w_hi <= w_lo) return OXG_OK;
+    const uint64_t base0 = offsets[0];
+    const uint64_t first = w_lo & ~(uint64_t)(kTileW - 1);
+    const uint64_t n_chunks = (w_hi - first + kChunkBytes - 1) / kChunkBytes;
+    const uint64_t stage_bytes = kChunkBytes + 256 + 16;
+    for (int b = 0; b < 2; ++b) {
+        if (!c->d_stage[b]) CU(cudaMalloc(&c->d_stage[b], stage_bytes));
+        if (!src_pinned && !c->h_stage[b]) CU(cudaMallocHost(&c->h_stage[b], stage_bytes));
+    }
+    auto issue_copy = [&](uint64_t ci) -> oxg_status {
+        const int b = (int)(ci & 1);
+        const uint64_t lo = first + ci * kChunkBytes;
+        const uint64_t hi = std::min(data_end, lo + kChunkBytes + k - 1);
+        // reads whose boundaries can fall inside [lo, hi + 1]
+        const uint64_t *ob = std::lower_bound(offsets, offsets + n_reads + 1, base0 + lo + 1);
+        const uint64_t *oe = std::upper_bound(offsets, offsets + n_reads + 1, base0 + hi + 1);
+        const uint64_t n_off = (uint64_t)(oe - ob);
+        if (c->offs_cap[b] < n_off + 1) {
+            if (c->d_offs[b]) CU(cudaFree(c->d_offs[b]));
+            if (c->h_offs[b]) CU(cudaFreeHost(c->h_offs[b]));
+            c->d_offs[b] = nullptr; c->h_offs[b] = nullptr; c->offs_cap[b] = 0;
+            const uint64_t ncap = std::max<uint64_t>(n_off + 1, 1 << 16);
+            CU(cudaMalloc(&c->d_offs[b], ncap * 8));
+            CU(cudaMallocHost(&c->h_offs[b], ncap * 8));
+            c->offs_cap[b] = ncap;
+        }
+        CU(cudaEventSynchronize(c->ev_free[b]));
+        for (uint64_t i = 0; i < n_off; ++i) c->h_offs[b][i] = ob[i] - base0;  // batch-relative positions
+        c->h_offs[b][n_off] = ~0ULL >> 1;  // sentinel keeps n_off >= 1
+        const uint8_t *src = bases + base0 + lo;
+        if (!src_pinned) { memcpy(c->h_stage[b], src, hi - lo); src = c->h_stage[b]; }
+        CU(cudaMemcpyAsync(c->d_stage[b], src, hi - lo, cudaMemcpyHostToDevice, c->copy));
+        CU(cudaMemcpyAsync(c->d_offs[b], c->h_offs[b], (n_off + 1) * 8, cudaMemcpyHostToDevice, c->copy));
+        CU(cudaEventRecord(c->ev_ready[b], c->copy));
+        return OXG_OK;
+    };
+    TRY(issue_copy(0));
+    for (uint64_t ci = 0; ci < n_chunks; ++ci) {
+        const int b = (int)(ci & 1);
+        const uint64_t lo = first + ci * kChunkBytes;
+        const uint64_t hi = std::min(data_end, lo + kChunkBytes + k - 1);
+        const uint64_t *ob = std::lower_bound(offsets, offsets + n_reads + 1, base0 + lo + 1);
+        const uint64_t *oe = std::upper_bound(offsets, offsets + n_reads + 1, base0 + hi + 1);
+        const uint64_t n_off = (uint64_t)(oe - ob) + 1;
+        CU(cudaStreamWaitEvent(c->stream, c->ev_ready[b], 0));
+        // run_span blocks on the stream after every launch, so the next chunk's staging
+        // (host memcpy into pinned memory + H2D on the copy stream) runs on a helper
+        // thread and overlaps this chunk's kernels
+        std::future<oxg_status> next;
+        if (ci + 1 < n_chunks) {
+            if (src_pinned) TRY(issue_copy(ci + 1));
+            else next = std::async(std::launch::async, [&, ci] { cudaSetDevice(c->dev); return issue_copy(ci + 1); });
+        }
+        oxg_status st = run_span(t, mode, c->d_stage[b], lo, std::max(lo, w_lo), std::min(w_hi, lo + kChunkBytes), hi,
+                                 c->d_offs[b], n_off, nullptr, counted);
+        if (next.valid()) {
+            oxg_status st2 = next.get();
+            if (st == OXG_OK && st2 != OXG_OK) st = fail(st2, "staging copy failed");
+        }
+        TRY(st);
+        CU(cudaEventRecord(c->ev_free[b], c->stream));
+    }
+    return OXG_OK;
+}
+
+oxg_status oxg_consume_batch(oxg_table *t, const uint8_t *bases, const uint64_t *offsets,
+                             uint64_t n_reads, int skip_bad, uint64_t *total_counted,
+                             int64_t *err_read, uint64_t *err_pos) {
+    ENTER(t);
+    if (total_counted) *total_counted = 0;
+    if (err_read) *err_read = -1;
+    if (err_pos) *err_pos = 0;
+    if (n_reads == 0) return OXG_OK;
+    if (!bases || !offsets) return fail(OXG_ERR_INVALID, "null argument");
+    for (uint64_t r = 0; r < n_reads; ++r)
+        if (offsets[r + 1] < offsets[r]) return fail(OXG_ERR_INVALID, "offsets must be non-decreasing");
+    const uint64_t k = t->k;
+    const uint64_t total = offsets[n_reads] - offsets[0];
+    const uint64_t n_win = total >= k ? total - k + 1 : 0;
+    t->last_ms = 0.f; t->last_launches = 0;
+    if (n_win == 0) return OXG_OK;
+    cudaPointerAttributes attr{};
+    bool pinned = cudaPointerGetAttributes(&attr, bases) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    uint64_t counted = 0;
+    oxg_status ret = OXG_OK;
+    if (skip_bad) {
+        TRY(stream_span(t, kModeCount, bases, offsets, n_reads, 0, n_win, total, pinned, &counted));
+    } else {
+        t->h_ctrl->first_bad = ~0ULL;
+        CU(cudaMemcpyAsync(&t->d_ctrl->first_bad, &t->h_ctrl->first_bad, 8, cudaMemcpyHostToDevice, c->stream));
+        TRY(stream_span(t, kModeFirstBad, bases, offsets, n_reads, 0, n_win, total, pinned, nullptr));
+        TRY(pull_ctrl(t));
+        const uint64_t fb = t->h_ctrl->first_bad;
+        if (fb == ~0ULL) {
+            TRY(stream_span(t, kModeCount, bases, offsets, n_reads, 0, n_win, total, pinned, &counted));
+        } else {
+            const uint64_t base0 = offsets[0];
+            const uint64_t r = (uint64_t)(std::upper_bound(offsets, offsets + n_reads + 1, base0 + fb) - offsets) - 1;
+            const uint64_t r_start = offsets[r] - base0;
+            uint64_t in_read = 0;
+            TRY(stream_span(t, kModeCount, bases, offsets, n_reads, 0, r_start >= k ? r_start - k + 1 : 0, r_start, pinned, &counted));
+            TRY(stream_span(t, kModeCount, bases, offsets, n_reads, r_start, fb, fb + k - 1, pinned, &in_read));
+            counted += in_read;
+            if (err_read) *err_read = (int64_t)r;
+            if (err_pos) *err_pos = in_read;
+            ret = fail(OXG_ERR_BAD_KMER, "bad k-mer encountered at position %llu", (unsigned long long)in_read);
+        }
+    }
+    if (total_counted) *total_counted = counted;
+    return ret;
+}
+
+// ---- by-hash operations ----------------------------------------------------
+
+oxg_status oxg_count_hashes_device(oxg_table *t, const uint64_t *d_hashes, uint64_t n) {
+    ENTER(t);
+    if (n == 0) return OXG_OK;
+    TRY(reserve_keys(t, n));
+    count_hashes_kernel<<<grid_for(c, n, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), d_hashes, n, nullptr);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return pull_ctrl(t);
+}
+
+oxg_status oxg_count_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, uint64_t *new_counts) {
+    ENTER(t);
+    if (n == 0) return OXG_OK;
+    if (!hashes) return fail(OXG_ERR_INVALID, "null argument");
+    TRY(reserve_keys(t, n));
+    TRY(ensure_io(c, 2 * n));
+    memcpy(c->h_io, hashes, n * 8);
+    CU(cudaMemcpyAsync(c->d_io, c->h_io, n * 8, cudaMemcpyHostToDevice, c->stream));
+    count_hashes_kernel<<<grid_for(c, n, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_io, n, new_counts ? c->d_io + n : nullptr);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    if (new_counts) CU(cudaMemcpyAsync(c->h_io + n, c->d_io + n, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    TRY(pull_ctrl(t));
+    if (new_counts) memcpy(new_counts, c->h_io + n, n * 8);
+    return OXG_OK;
+}
+
+oxg_status oxg_get_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, uint64_t *counts_out) {
+    ENTER(t);
+    if (n == 0) return OXG_OK;
+    if (!hashes || !counts_out) return fail(OXG_ERR_INVALID, "null argument");
+    TRY(ensure_io(c, 2 * n));
+    memcpy(c->h_io, hashes, n * 8);
+    CU(cudaMemcpyAsync(c->d_io, c->h_io, n * 8, cudaMemcpyHostToDevice, c->stream));
+    get_hashes_kernel<<<grid_for(c, n, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_io, n, c->d_io + n);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_io + n, c->d_io + n, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(counts_out, c->h_io + n, n * 8);
+    return OXG_OK;
+}
+
+oxg_status oxg_set_hash(oxg_table *t, uint64_t hash, uint64_t value) {
+    ENTER(t);
+    TRY(reserve_keys(t, 1));
+    set_hash_kernel<<<1, 32, 0, c->stream>>>(view_of(t, false), hash, value);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return pull_ctrl(t);
+}
+
+oxg_status oxg_erase_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, uint64_t *n_removed) {
+    ENTER(t);
+    if (n_removed) *n_removed = 0;
+    if (n == 0) return OXG_OK;
+    if (!hashes) return fail(OXG_ERR_INVALID, "null argument");
+    TRY(ensure_io(c, n));
+    memcpy(c->h_io, hashes, n * 8);
+    CU(cudaMemcpyAsync(c->d_io, c->h_io, n * 8, cudaMemcpyHostToDevice, c->stream));
+    erase_hashes_kernel<<<1, 32, 0, c->stream>>>(view_of(t, false), c->d_io, n);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    TRY(pull_ctrl(t));
+    if (n_removed) *n_removed = t->h_ctrl->scratch[0];
+    return OXG_OK;
+}
+
+oxg_status oxg_cut(oxg_table *t, int mode, uint64_t thresh, uint64_t *n_removed) {
+    ENTER(t);
+    if (mode != 0 && mode != 1) return fail(OXG_ERR_INVALID, "mode must be 0 (mincut) or 1 (maxcut)");
+    TRY(pull_ctrl(t));
+    uint64_t removed = 0;
+    ulonglong2 *fresh = nullptr;
+    TRY(alloc_slots(c, t->cap, &fresh));
+    ulonglong2 *old = t->slots;
+    t->slots = fresh;
+    TRY(zero_ctrl_fields(t, kFieldScratch, 1));
+    cut_kernel<<<grid_for(c, t->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(old, t->cap, view_of(t, false), mode, thresh);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    TRY(pull_ctrl(t));
+    CU(cudaFree(old));
+    removed = t->h_ctrl->scratch[0];
+    t->h_ctrl->size -= removed;
+    if (t->h_ctrl->side_present) {
+        const uint64_t v = t->h_ctrl->side_count;
+        if (mode == 0 ? v < thresh : v > thresh) { t->h_ctrl->side_present = 0; t->h_ctrl->side_count = 0; ++removed; }
+    }
+    t->size = t->h_ctrl->size;
+    CU(cudaMemcpyAsync(t->d_ctrl, t->h_ctrl, offsetof(Ctrl, counted), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (n_removed) *n_removed = removed;
+    return OXG_OK;
+}
+
+// ---- scans -------------------------------------------------------------------
+
+static oxg_status run_stats(oxg_table *t, bool histo, oxg_stats *st, uint64_t *n_big) {
+    DeviceCtx *c = t->ctx;
+    if (histo) {
+        CU(cudaMemsetAsync(c->d_dense, 0, kHistDense * 8, c->stream));
+        if (!c->d_big) TRY(ensure_dev(&c->d_big, &c->big_cap, 1 << 16));
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        Ctrl init{};
+        init.scratch[2] = ~0ULL;
+        memcpy(t->h_ctrl->scratch, init.scratch, sizeof init.scratch);
+        CU(cudaMemcpyAsync(t->d_ctrl->scratch, t->h_ctrl->scratch, sizeof init.scratch, cudaMemcpyHostToDevice, c->stream));
+        stats_kernel<<<grid_for(c, t->cap, kOpThreads, 8), kOpThreads, 0, c->stream>>>(view_of(t, false), histo ? c->d_dense : nullptr, c->d_big, c->big_cap);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        TRY(pull_ctrl(t));
+        if (!histo || t->h_ctrl->scratch[4] <= c->big_cap) break;
+        // more huge counts than the list holds: enlarge and redo
+        TRY(ensure_dev(&c->d_big, &c->big_cap, t->h_ctrl->scratch[4]));
+        CU(cudaMemsetAsync(c->d_dense, 0, kHistDense * 8, c->stream));
+    }
+    const Ctrl *h = t->h_ctrl;
+    st->len = h->scratch[0]; st->sum = h->scratch[1];
+    st->min = h->scratch[0] ? h->scratch[2] : ~0ULL; st->max = h->scratch[3];
+    if (h->side_present) {
+        st->len += 1; st->sum += h->side_count;
+        st->min = std::min(st->min, h->side_count); st->max = std::max(st->max, h->side_count);
+    }
+    if (st->len == 0) { st->min = 0; st->max = 0; }
+    if (n_big) *n_big = h->scratch[4];
+    return OXG_OK;
+}
+
+oxg_status oxg_table_len(oxg_table *t, uint64_t *len) {
+    ENTER(t);
+    if (!len) return fail(OXG_ERR_INVALID, "null argument");
+    TRY(pull_ctrl(t));
+    *len = t->h_ctrl->size + (t->h_ctrl->side_present ? 1 : 0);
+    return OXG_OK;
+}
+
+oxg_status oxg_table_stats(oxg_table *t, oxg_stats *out) {
+    ENTER(t);
+    if (!out) return fail(OXG_ERR_INVALID, "null argument");
+    return run_stats(t, false, out, nullptr);
+}
+
+oxg_status oxg_histo(oxg_table *t, uint64_t *freq, uint64_t *n, uint64_t cap, uint64_t *n_out) {
+    ENTER(t);
+    if (!n_out) return fail(OXG_ERR_INVALID, "null argument");
+    oxg_stats st;
+    uint64_t n_big = 0;
+    TRY(run_stats(t, true, &st, &n_big));
+    std::vector<uint64_t> dense(kHistDense), big(n_big);
+    CU(cudaMemcpyAsync(dense.data(), c->d_dense, kHistDense * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (n_big) CU(cudaMemcpyAsync(big.data(), c->d_big, n_big * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (t->h_ctrl->side_present) {
+        const uint64_t v = t->h_ctrl->side_count;
+        if (v < kHistDense) dense[v] += 1; else big.push_back(v);
+    }
+    std::sort(big.begin(), big.end());
+    uint64_t w = 0, total = 0;
+    auto emit = [&](uint64_t f, uint64_t cnt) {
+        if (w < cap && freq && n) { freq[w] = f; n[w] = cnt; ++w; }
+        ++total;
+    };
+    for (uint64_t f = 0; f < kHistDense; ++f) if (dense[f]) emit(f, dense[f]);
+    for (size_t i = 0; i < big.size();) {
+        size_t j = i;
+        while (j < big.size() && big[j] == big[i]) ++j;
+        emit(big[i], j - i);
+        i = j;
+    }
+    *n_out = total;
+    return OXG_OK;
+}
+
+// ---- export --------------------------------------------------------------------
+
+static oxg_status export_device(oxg_table *t, uint64_t **d_keys, uint64_t **d_vals, uint64_t *n_live) {
+    DeviceCtx *c = t->ctx;
+    const uint64_t n_chunks = (t->cap + kExportChunk - 1) / kExportChunk;
+    uint64_t *d_counts = nullptr;
+    CU(cudaMalloc(&d_counts, (n_chunks + 1) * 8));
+    export_count_kernel<<<(unsigned)n_chunks, kOpThreads, 0, c->stream>>>(t->slots, t->cap, d_counts);
+    LAUNCHED();
+    export_scan_kernel<<<1, 1024, 0, c->stream>>>(d_counts, n_chunks, d_counts + n_chunks);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    uint64_t live = 0;
+    CU(cudaMemcpyAsync(&live, d_counts + n_chunks, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMalloc(d_keys, std::max<uint64_t>(live, 1) * 8));
+    CU(cudaMalloc(d_vals, std::max<uint64_t>(live, 1) * 8));
+    export_write_kernel<<<(unsigned)n_chunks, kOpThreads, 0, c->stream>>>(t->slots, t->cap, d_counts, *d_keys, *d_vals, live);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(d_counts));
+    *n_live = live;
+    return OXG_OK;
+}
+
+oxg_status oxg_export(oxg_table *t, uint64_t *keys, uint64_t *vals, uint64_t cap, int sort_mode, uint64_t *n_out) {
+    ENTER(t);
+    if (!n_out) return fail(OXG_ERR_INVALID, "null argument");
+    if (sort_mode < 0 || sort_mode > 2) return fail(OXG_ERR_INVALID, "sort_mode must be 0, 1 or 2");
+    TRY(pull_ctrl(t));
+    const bool side = t->h_ctrl->side_present != 0;
+    const uint64_t total = t->h_ctrl->size + (side ? 1 : 0);
+    *n_out = total;
+    if (cap == 0 || total == 0) return OXG_OK;
+    uint64_t *d_keys = nullptr, *d_vals = nullptr, live = 0;
+    TRY(export_device(t, &d_keys, &d_vals, &live));
+    std::vector<uint64_t> hk(live + 1), hv(live + 1);
+    if (live) {
+        CU(cudaMemcpy(hk.data(), d_keys, live * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(hv.data(), d_vals, live * 8, cudaMemcpyDeviceToHost));
+    }
+    CU(cudaFree(d_keys));
+    CU(cudaFree(d_vals));
+    uint64_t n = live;
+    if (side) { hk[n] = kEmpty; hv[n] = t->h_ctrl->side_count; ++n; }
+    if (sort_mode != 0) {
+        std::vector<uint64_t> order(n);
+        for (uint64_t i = 0; i < n; ++i) order[i] = i;
+        if (sort_mode == 1) std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hk[a] < hk[b]; });
+        else std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hv[a] != hv[b] ? hv[a] < hv[b] : hk[a] < hk[b]; });
+        for (uint64_t i = 0; i < std::min(n, cap); ++i) { if (keys) keys[i] = hk[order[i]]; if (vals) vals[i] = hv[order[i]]; }
+    } else {
+        for (uint64_t i = 0; i < std::min(n, cap); ++i) { if (keys) keys[i] = hk[i]; if (vals) vals[i] = hv[i]; }
+    }
+    return OXG_OK;
+}
+
+// ---- set comparisons -------------------------------------------------------------
+
+static oxg_status two_tables(oxg_table *a, oxg_table *b) {
+    if (!a || !b) return fail(OXG_ERR_INVALID, "table is null");
+    if (a->ctx != b->ctx) return fail(OXG_ERR_INVALID, "tables live on different devices");
+    return OXG_OK;
+}
+
+static oxg_status setop_sizes_locked(oxg_table *a, oxg_table *b, uint64_t *inter, uint64_t *uni) {
+    DeviceCtx *c = a->ctx;
+    TRY(pull_ctrl(b));
+    TRY(zero_ctrl_fields(a, kFieldScratch, 1));
+    setop_count_kernel<<<grid_for(c, a->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(a, false), view_of(b, false));
+    LAUNCHED();
+    CU(cudaGetLastError());
+    TRY(pull_ctrl(a));
+    uint64_t both = a->h_ctrl->scratch[0];
+    if (a->h_ctrl->side_present && b->h_ctrl->side_present) both += 1;
+    const uint64_t na = a->h_ctrl->size + (a->h_ctrl->side_present ? 1 : 0);
+    const uint64_t nb = b->h_ctrl->size + (b->h_ctrl->side_present ? 1 : 0);
+    if (inter) *inter = both;
+    if (uni) *uni = na + nb - both;
+    return OXG_OK;
+}
+
+oxg_status oxg_setop_sizes(oxg_table *a, oxg_table *b, uint64_t *inter, uint64_t *uni) {
+    TRY(two_tables(a, b));
+    ENTER(a);
+    return setop_sizes_locked(a, b, inter, uni);
+}
+
+oxg_status oxg_jaccard(oxg_table *a, oxg_table *b, double *out) {
+    TRY(two_tables(a, b));
+    ENTER(a);
+    if (!out) return fail(OXG_ERR_INVALID, "null argument");
+    uint64_t inter = 0, uni = 0;
+    TRY(setop_sizes_locked(a, b, &inter, &uni));
+    *out = uni == 0 ? 1.0 : (double)inter / (double)uni;  // src/lib.rs:716-721
+    return OXG_OK;
+}
+
+oxg_status oxg_setop_export(oxg_table *a, oxg_table *b, int op, uint64_t *keys_out, uint64_t cap, uint64_t *n_out) {
+    TRY(two_tables(a, b));
+    ENTER(a);
+    if (!n_out) return fail(OXG_ERR_INVALID, "null argument");
+    if (op < 0 || op > 3) return fail(OXG_ERR_INVALID, "unknown set operation %d", op);
+    TRY(pull_ctrl(a));
+    TRY(pull_ctrl(b));
+    const uint64_t room = a->h_ctrl->size + b->h_ctrl->size + 2;
+    uint64_t *d_out = nullptr, *d_cnt = nullptr;
+    CU(cudaMalloc(&d_out, room * 8));
+    CU(cudaMalloc(&d_cnt, 8));
+    CU(cudaMemsetAsync(d_cnt, 0, 8, c->stream));
+    auto pass = [&](oxg_table *x, oxg_table *y, int want) -> oxg_status {
+        setop_export_kernel<<<grid_for(c, x->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(x, false), view_of(y, false), want, d_out, room, d_cnt);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        return OXG_OK;
+    };
+    switch (op) {
+    case OXG_UNION: TRY(pass(a, b, 2)); TRY(pass(b, a, 0)); break;
+    case OXG_INTERSECTION: TRY(pass(a, b, 1)); break;
+    case OXG_DIFFERENCE: TRY(pass(a, b, 0)); break;
+    default: TRY(pass(a, b, 0)); TRY(pass(b, a, 0)); break;
+    }
+    uint64_t n = 0;
+    CU(cudaMemcpyAsync(&n, d_cnt, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<uint64_t> host(n + 1);
+    if (n) CU(cudaMemcpy(host.data(), d_out, n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaFree(d_out));
+    CU(cudaFree(d_cnt));
+    // the out-of-band key
+    const bool sa = a->h_ctrl->side_present, sb = b->h_ctrl->side_present;
+    bool side = false;
+    switch (op) {
+    case OXG_UNION: side = sa || sb; break;
+    case OXG_INTERSECTION: side = sa && sb; break;
+    case OXG_DIFFERENCE: side = sa && !sb; break;
+    default: side = sa != sb; break;
+    }
+    if (side) host[n++] = kEmpty;
+    *n_out = n;
+    if (keys_out) memcpy(keys_out, host.data(), std::min(n, cap) * 8);
+    return OXG_OK;
+}
+
+oxg_status oxg_cosine(oxg_table *a, oxg_table *b, double *out) {
+    TRY(two_tables(a, b));
+    ENTER(a);
+    if (!out) return fail(OXG_ERR_INVALID, "null argument");
+    TRY(pull_ctrl(a));
+    TRY(pull_ctrl(b));
+    const uint64_t na = a->h_ctrl->size + (a->h_ctrl->side_present ? 1 : 0);
+    const uint64_t nb = b->h_ctrl->size + (b->h_ctrl->side_present ? 1 : 0);
+    if (na == 0 || nb == 0) { *out = 0.0; return OXG_OK; }  // src/lib.rs:729-731
+    CU(cudaMemsetAsync(c->d_f64, 0, 4 * sizeof(double), c->stream));
+    TRY(zero_ctrl_fields(a, kFieldScratch, 1));
+    cosine_kernel<<<grid_for(c, a->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(a, false), view_of(b, false), c->d_f64);
+    LAUNCHED();
+    TableView none = view_of(a, false);
+    none.slots = nullptr;
+    TRY(zero_ctrl_fields(b, kFieldScratch, 1));
+    cosine_kernel<<<grid_for(c, b->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(b, false), none, c->d_f64 + 1);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    double sq[2];
+    CU(cudaMemcpyAsync(sq, c->d_f64, 16, cudaMemcpyDeviceToHost, c->stream));
+    TRY(pull_ctrl(a));
+    uint64_t dot = a->h_ctrl->scratch[0];
+    if (a->h_ctrl->side_present) {
+        sq[0] += (double)a->h_ctrl->side_count * (double)a->h_ctrl->side_count;
+        if (b->h_ctrl->side_present) dot += a->h_ctrl->side_count * b->h_ctrl->side_count;
+    }
+    if (b->h_ctrl->side_present) sq[1] += (double)b->h_ctrl->side_count * (double)b->h_ctrl->side_count;
+    const double ma = sqrt(sq[0]), mb = sqrt(sq[1]);
+    *out = (ma == 0.0 || mb == 0.0) ? 0.0 : (double)dot / (ma * mb);
+    return OXG_OK;
+}
+
+oxg_status oxg_merge(oxg_table *dst, oxg_table *src, uint64_t *counts_added, uint64_t *new_keys) {
+    TRY(two_tables(dst, src));
+    if (dst == src) return fail(OXG_ERR_INVALID, "cannot merge a table into itself");
+    if (dst->k != src->k) return fail(OXG_ERR_WRONG_KSIZE, "KmerCountTables must have the same ksize");
+    ENTER(dst);
+    TRY(pull_ctrl(dst));
+    TRY(pull_ctrl(src));
+    TRY(reserve_keys(dst, src->h_ctrl->size));
+    TRY(zero_ctrl_fields(dst, kFieldScratch, 2));
+    merge_kernel<<<grid_for(c, src->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(dst, false), view_of(src, false));
+    LAUNCHED();
+    CU(cudaGetLastError());
+    TRY(pull_ctrl(dst));
+    uint64_t added = dst->h_ctrl->scratch[0], fresh = dst->h_ctrl->scratch[1];
+    if (src->h_ctrl->side_present) {
+        Ctrl *h = dst->h_ctrl;
+        if (!h->side_present || h->side_count == 0) ++fresh;
+        h->side_present = 1;
+        h->side_count += src->h_ctrl->side_count;
+        added += src->h_ctrl->side_count;
+        CU(cudaMemcpyAsync(&dst->d_ctrl->side_present, &h->side_present, 16, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    if (counts_added) *counts_added = added;
+    if (new_keys) *new_keys = fresh;
+    return OXG_OK;
+}
+
+// ---- multi-GPU routing ------------------------------------------------------------
+
+oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const uint64_t *d_offsets,
+                                  uint64_t n_reads, uint64_t total_bases, int n_ranks, int self_rank,
+                                  uint64_t *const *d_out, uint64_t out_cap, uint64_t *d_out_counts,
+                                  uint64_t *out_counts, uint64_t *local_counted) {
+    ENTER(t);
+    if (n_ranks < 1 || n_ranks > kMaxRanks || (n_ranks & (n_ranks - 1)))
+        return fail(OXG_ERR_INVALID, "n_ranks must be a power of two <= %d", kMaxRanks);
+    if (self_rank < 0 || self_rank >= n_ranks) return fail(OXG_ERR_INVALID, "self_rank out of range");
+    if (local_counted) *local_counted = 0;
+    const uint64_t k = t->k;
+    CU(cudaMemsetAsync(d_out_counts, 0, (size_t)n_ranks * 8, c->stream));
+    t->last_ms = 0.f; t->last_launches = 0;
+    uint64_t counted = 0;
+    const uint64_t n_win = total_bases >= k ? total_bases - k + 1 : 0;
+    int lg = 0;
+    while ((1 << lg) < n_ranks) ++lg;
+    uint64_t lo = 0;
+    while (lo < n_win) {
+        const uint64_t hi = std::min(n_win, lo + kLaunchWindows);
+        const uint64_t n_tiles = (hi - lo + kTileW - 1) / kTileW;
+        TRY(ensure_dev(&c->d_tile_first, &c->tile_first_cap, n_tiles));
+        if (t->size * 2 > t->cap) TRY(grow_to_fit(t, t->size * 2));
+        TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, hi - lo));
+        TRY(zero_ctrl_fields(t, kFieldCounted, 2));
+        ConsumeParams p{};
+        p.bases = d_bases; p.g0 = 0; p.w_lo = lo; p.w_hi = hi; p.data_end = total_bases;
+        p.tile_base = lo; p.n_tiles = n_tiles; p.offsets = d_offsets; p.n_off = n_reads + 1;
+        p.tile_first = c->d_tile_first; p.table = view_of(t, true); p.ksize = t->k;
+        p.owner_shift = lg == 0 ? 63 : 64 - lg;  // with one rank every hash >> 63 is 0 or 1; handled below
+        p.self_rank = self_rank;
+        for (int r = 0; r < n_ranks; ++r) p.route_out[r] = d_out ? d_out[r] : nullptr;
+        p.route_counts = d_out_counts; p.route_cap = out_cap;
+        if (lg == 0) return fail(OXG_ERR_INVALID, "use oxg_consume_batch_device when n_ranks == 1");
+        tile_first_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(d_offsets, n_reads + 1, lo, n_tiles, c->d_tile_first);
+        LAUNCHED();
+        CU(cudaEventRecord(c->ev_t0, c->stream));
+        TRY(launch_consume<kModeRoute>(t, p));
+        CU(cudaEventRecord(c->ev_t1, c->stream));
+        TRY(pull_ctrl(t));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+        t->last_ms += ms; t->last_launches += 1;
+        counted += t->h_ctrl->counted;
+        const uint64_t ov = t->h_ctrl->overflow;
+        if (ov) {
+            TRY(grow_to_fit(t, t->size + ov));
+            count_hashes_kernel<<<grid_for(c, ov, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr);
+            LAUNCHED();
+            CU(cudaGetLastError());
+            TRY(pull_ctrl(t));
+        }
+        lo = hi;
+    }
+    if (out_counts) {
+        CU(cudaMemcpyAsync(out_counts, d_out_counts, (size_t)n_ranks * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < n_ranks; ++r)
+            if (out_counts[r] > out_cap) return fail(OXG_ERR_TOO_SMALL, "outgoing list for rank %d overran (%llu > %llu)", r, (unsigned long long)out_counts[r], (unsigned long long)out_cap);
+    }
+    if (local_counted) *local_counted = counted;
+    return OXG_OK;
+}
+
+// ---- synthetic reads, memory helpers ------------------------------------------------
+
+oxg_status oxg_synth_reads_device(int device, uint8_t *d_bases, uint64_t n_reads, uint32_t read_len,
+                                  uint64_t genome_len, uint64_t seed, uint64_t first_read,
+                                  uint32_t sub_ppm, uint32_t n_ppm) {
+    DeviceCtx *c;
+    TRY(get_ctx(device, &c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->dev));
+    if (!d_bases || read_len == 0 || genome_len < read_len) return fail(OXG_ERR_INVALID, "bad synth arguments");
+    synth_reads_kernel<<<c->sms * 16, 256, 0, c->stream>>>(d_bases, n_reads, read_len, genome_len, seed, first_read, sub_ppm, n_ppm);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return OXG_OK;
+}
+
+oxg_status oxg_pinned_alloc(uint64_t bytes, void **out) {
+    if (!out) return fail(OXG_ERR_INVALID, "null argument");
+    CU(cudaMallocHost(out, bytes ? bytes : 1));
+    return OXG_OK;
+}
+oxg_status oxg_pinned_free(void *p) {
+    if (p) CU(cudaFreeHost(p));
+    return OXG_OK;
+}
+oxg_status oxg_device_alloc(int device, uint64_t bytes, void **d_out) {
+    DeviceCtx *c;
+    TRY(get_ctx(device, &c));
+    CU(cudaSetDevice(c->dev));
+    CU(cudaMalloc(d_out, bytes ? bytes : 16));
+    return OXG_OK;
+}
+oxg_status oxg_device_free(int device, void *d_ptr) {
+    DeviceCtx *c;
+    TRY(get_ctx(device, &c));
+    CU(cudaSetDevice(c->dev));
+    if (d_ptr) CU(cudaFree(d_ptr));
+    return OXG_OK;
+}
+oxg_status oxg_memcpy_h2d(int device, void *d_dst, const void *src, uint64_t bytes) {
+    DeviceCtx *c;
+    TRY(get_ctx(device, &c));
+    CU(cudaSetDevice(c->dev));
+    CU(cudaMemcpy(d_dst, src, bytes, cudaMemcpyHostToDevice));
+    return OXG_OK;
+}
+oxg_status oxg_memcpy_d2h(int device, void *dst, const void *d_src, uint64_t bytes) {
+    DeviceCtx *c;
+    TRY(get_ctx(device, &c));
+    CU(cudaSetDevice(c->dev));
+    CU(cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return OXG_OK;
+}
+
+}  // extern "C"

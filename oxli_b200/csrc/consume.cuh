@@ -1,0 +1,386 @@
+// consume.cuh -- the sliding-window kernels (K1 fused with K2).
+//
+// Replaces the hot loop of KmerCountTable::consume
+// (/root/reference/src/lib.rs:576-600): SeqToHashes iterator step (validity,
+// canonical choice, murmur) + `count_hash` per window.
+//
+// Work decomposition: the batch is one flat byte stream; every position is a
+// candidate window start.  A CTA takes tiles of kTileW consecutive starts
+// (+K-1 bytes of halo), stages them once in shared memory as
+//   s_fw : upper-cased bytes                     (forward strand)
+//   s_rc : complemented bytes, mirrored           (reverse strand, so the
+//          reverse complement of any window is again a contiguous byte run)
+//   s_bad: 1 bit per byte, set for non-ACGT / past-the-end bytes
+//   s_end: 1 bit per byte, set on the last base of a read (CSR boundary)
+// and each thread then owns kWPT consecutive windows: it pulls Q bytes per
+// strand with 64-bit shared loads, derives each window's words with constant
+// funnel shifts, decides fw-vs-rc on the byte-swapped leading word (full
+// compare only on a tie), hashes, and probes the table.  A window is counted
+// iff no bad bit lies in [p,p+K) and no end bit in [p,p+K-1).
+#pragma once
+#include <utility>
+
+#include "hashing.cuh"
+#include "table.cuh"
+
+namespace oxg {
+
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, I...>) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+// f(integral_constant<int, 0>) ... f(integral_constant<int, N-1>), fully unrolled
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f) {
+    static_for_impl(f, std::make_integer_sequence<int, N>{});
+}
+
+constexpr int kTileW = 2048;  // window starts per tile
+constexpr int kThreads = 256;
+constexpr int kWPT = kTileW / kThreads;  // 8 consecutive windows per thread
+static_assert(kWPT == 8, "bit-mask extraction assumes 8 windows per thread");
+constexpr int kMaxRanks = 16;
+
+enum Mode : int {
+    kModeCount = 0,    // hash + count into the table
+    kModeHash = 1,     // hash only, write one u64 per window (0 = bad window)
+    kModeFirstBad = 2, // error-mode pre-scan: smallest in-read window holding a bad byte
+    kModeRoute = 3     // multi-GPU: count hashes owned by this rank, append the rest per owner
+};
+
+struct ConsumeParams {
+    const uint8_t *bases;  // device; bases[0] is global byte position g0 (16-byte aligned)
+    uint64_t g0;
+    uint64_t w_lo, w_hi;   // window starts handled by this launch
+    uint64_t data_end;     // one past the last byte that may be read / belongs to the batch
+    uint64_t tile_base;    // global start of tile 0: multiple of 16, g0 <= tile_base <= w_lo
+    uint64_t n_tiles;
+    const uint64_t *offsets;  // CSR offsets (global positions), n_off entries, ascending
+    uint64_t n_off;
+    const uint64_t *tile_first;  // per tile: first index r with offsets[r] > tile start
+    TableView table;
+    uint64_t *hashes_out;  // kModeHash: hashes_out[w - w_lo]
+    uint32_t ksize;        // generic kernel only
+    // kModeRoute
+    int owner_shift;       // owner(h) = h >> owner_shift
+    int self_rank;
+    uint64_t *route_out[kMaxRanks];
+    uint64_t *route_counts;
+    uint64_t route_cap;
+};
+
+__global__ void tile_first_kernel(const uint64_t *__restrict__ offsets, uint64_t n_off,
+                                  uint64_t tile_base, uint64_t n_tiles,
+                                  uint64_t *__restrict__ tile_first) {
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const uint64_t want = tile_base + t * kTileW + 1;  // first offsets[r] >= want
+    uint64_t lo = 0, hi = n_off;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (offsets[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    tile_first[t] = lo;
+}
+
+__device__ __forceinline__ uint4 load_bases16(const ConsumeParams &p, uint64_t g) {
+    if (g + 16 <= p.data_end) {
+        return __ldcs(reinterpret_cast<const uint4 *>(p.bases + (g - p.g0)));
+    }
+    uint32_t w[4] = {0x4e4e4e4eu, 0x4e4e4e4eu, 0x4e4e4e4eu, 0x4e4e4e4eu};  // 'N'
+    for (int b = 0; b < 16; ++b) {
+        if (g + b < p.data_end) {
+            uint32_t c = p.bases[g + b - p.g0];
+            w[b >> 2] = (w[b >> 2] & ~(0xffu << (8 * (b & 3)))) | (c << (8 * (b & 3)));
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Stage 16 bytes: forward bytes at s_fw[16v..], mirrored complement at
+// s_rc[BL-16-16v ..], 16 bad bits at s_bad[v].
+template <int BL>
+__device__ __forceinline__ void stage16(const ConsumeParams &p, uint64_t w0, int v, uint8_t *s_fw,
+                                        uint8_t *s_rc, uint16_t *s_bad) {
+    const uint64_t g = w0 + 16ull * v;
+    uint4 raw = load_bases16(p, g);
+    uint32_t u[4] = {upper4(raw.x), upper4(raw.y), upper4(raw.z), upper4(raw.w)};
+    uint32_t ok = acgt_mask4(u[0]) | (acgt_mask4(u[1]) << 4) | (acgt_mask4(u[2]) << 8) |
+                  (acgt_mask4(u[3]) << 12);
+    if (g + 16 > p.data_end) {  // bytes past the end are bad whatever they hold
+        uint32_t keep = g >= p.data_end ? 0u : (0xffffu >> (16 - (uint32_t)(p.data_end - g)));
+        ok &= keep;
+    }
+    *reinterpret_cast<uint4 *>(s_fw + 16 * v) = make_uint4(u[0], u[1], u[2], u[3]);
+    *reinterpret_cast<uint4 *>(s_rc + BL - 16 - 16 * v) =
+        make_uint4(bswap32(complement4(u[3])), bswap32(complement4(u[2])),
+                   bswap32(complement4(u[1])), bswap32(complement4(u[0])));
+    s_bad[v] = (uint16_t)(~ok);
+}
+
+template <int K, int MODE>
+__global__ void __launch_bounds__(kThreads) consume_kernel(const ConsumeParams p) {
+    static_assert(K >= 1 && K <= 32, "specialised kernel covers k <= 32");
+    constexpr int Q = 8 * ((K + 7 + 7) / 8);  // bytes a thread pulls per strand
+    constexpr int BL = ((kTileW - 8 + Q) + 15) / 16 * 16;
+    constexpr int NV = BL / 16;
+    constexpr int NX = Q / 8;
+    constexpr int NW = (K + 7) / 8;
+    constexpr uint64_t MK = K == 64 ? ~0ULL : ((1ULL << K) - 1);
+    constexpr uint64_t MK1 = (1ULL << (K - 1)) - 1;
+    constexpr uint64_t TAILMASK = (K % 8) ? (~0ULL >> (8 * (8 - K % 8))) : ~0ULL;
+
+    __shared__ __align__(16) uint8_t s_fw[BL];
+    __shared__ __align__(16) uint8_t s_rc[BL];
+    __shared__ __align__(8) uint16_t s_bad[NV + 6];
+    __shared__ __align__(8) uint32_t s_end[BL / 32 + 3];
+
+    const int tid = threadIdx.x;
+    uint64_t n_counted = 0;
+    uint64_t first_bad = ~0ULL;
+
+    for (uint64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const uint64_t w0 = p.tile_base + t * kTileW;
+        for (int i = tid; i < BL / 32 + 3; i += kThreads) s_end[i] = 0;
+        __syncthreads();
+
+        if (tid < NV) stage16<BL>(p, w0, tid, s_fw, s_rc, s_bad);
+        for (uint64_t r = p.tile_first[t] + tid; r < p.n_off; r += kThreads) {
+            const uint64_t e = p.offsets[r] - 1 - w0;  // last base of read r-1, tile-relative
+            if (e >= (uint64_t)BL) break;
+            atomicOr(&s_end[e >> 5], 1u << (e & 31));
+        }
+        bool full = false;
+        if (MODE == kModeCount || MODE == kModeRoute)
+            full = __ldcg(&p.table.ctrl->size) >= p.table.limit;
+        __syncthreads();
+
+        const int p0 = tid * kWPT;
+        const uint32_t *bad32 = reinterpret_cast<const uint32_t *>(s_bad);
+        const int wi = p0 >> 5, sh = p0 & 31;
+        const uint64_t mb = (((uint64_t)bad32[wi + 1] << 32) | bad32[wi]) >> sh;
+        const uint64_t me = (((uint64_t)s_end[wi + 1] << 32) | s_end[wi]) >> sh;
+        const uint64_t gp0 = w0 + p0;
+
+        uint32_t valid = 0;
+#pragma unroll
+        for (int j = 0; j < kWPT; ++j) {
+            const bool in_range = gp0 + j >= p.w_lo && gp0 + j < p.w_hi;
+            const bool in_read = ((me >> j) & MK1) == 0;
+            const bool clean = ((mb >> j) & MK) == 0;
+            if (MODE == kModeFirstBad) {
+                if (in_range && in_read && !clean && gp0 + j + K <= p.data_end)
+                    first_bad = min(first_bad, gp0 + j);
+            } else if (in_range && in_read && clean) {
+                valid |= 1u << j;
+            }
+        }
+
+        uint32_t created = 0;
+        if (MODE != kModeFirstBad) {
+            uint64_t h[kWPT];
+#pragma unroll
+            for (int j = 0; j < kWPT; ++j) h[j] = 0;
+            if (valid) {
+                uint64_t F[NX], R[NX];
+                const uint64_t *f64 = reinterpret_cast<const uint64_t *>(s_fw + p0);
+                const uint64_t *r64 = reinterpret_cast<const uint64_t *>(s_rc + BL - p0 - Q);
+#pragma unroll
+                for (int i = 0; i < NX; ++i) { F[i] = f64[i]; R[i] = r64[i]; }
+
+                auto hash_one = [&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    constexpr int FO = j, RO = Q - K - j;
+                    uint64_t a[NW], b[NW];
+                    static_for<NW>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        a[i] = word_at<FO + 8 * i>(F);
+                        b[i] = word_at<RO + 8 * i>(R);
+                    });
+                    a[NW - 1] &= TAILMASK;
+                    b[NW - 1] &= TAILMASK;
+                    bool use_rc = bswap64(b[0]) < bswap64(a[0]);
+                    if (NW > 1 && a[0] == b[0]) {  // rare: first 8 bases tie
+#pragma unroll
+                        for (int i = 1; i < NW; ++i) {
+                            if (a[i] != b[i]) { use_rc = bswap64(b[i]) < bswap64(a[i]); break; }
+                        }
+                    }
+                    uint64_t w[NW];
+#pragma unroll
+                    for (int i = 0; i < NW; ++i) w[i] = use_rc ? b[i] : a[i];
+                    h[j] = ((valid >> j) & 1u) ? murmur_words<K>(w) : 0;
+                };
+                static_for<kWPT>(hash_one);
+            }
+
+            if (MODE == kModeHash) {
+#pragma unroll
+                for (int j = 0; j < kWPT; ++j)
+                    if (gp0 + j >= p.w_lo && gp0 + j < p.w_hi) p.hashes_out[gp0 + j - p.w_lo] = h[j];
+            } else if (MODE == kModeCount) {
+                // issue all home-slot loads first (memory-level parallelism), then resolve
+                uint64_t idx[kWPT];
+                ulonglong2 s[kWPT];
+#pragma unroll
+                for (int j = 0; j < kWPT; ++j) idx[j] = p.table.home(h[j]);
+#pragma unroll
+                for (int j = 0; j < kWPT; ++j)
+                    if (h[j] != 0) s[j] = load_slot(p.table.slots + idx[j]);
+#pragma unroll
+                for (int j = 0; j < kWPT; ++j) {
+                    if (h[j] == 0) continue;  // bad window, or the reference's hash==0 skip
+                    ++n_counted;
+                    if (s[j].x == h[j]) red_add64(&p.table.slots[idx[j]].y, 1);
+                    else created += table_add(p.table, h[j], 1, full);
+                }
+            } else if (MODE == kModeRoute) {
+#pragma unroll
+                for (int j = 0; j < kWPT; ++j) {
+                    if (h[j] == 0) continue;
+                    const int owner = (int)(h[j] >> p.owner_shift);
+                    if (owner == p.self_rank) {
+                        ++n_counted;
+                        created += table_add(p.table, h[j], 1, full);
+                    } else {
+                        // warp-aggregated append to the owner's outgoing list
+                        const unsigned peers = __match_any_sync(__activemask(), owner);
+                        const int leader = __ffs(peers) - 1, lane = tid & 31;
+                        uint64_t base = 0;
+                        if (lane == leader)
+                            base = atomicAdd((unsigned long long *)&p.route_counts[owner],
+                                             (unsigned long long)__popc(peers));
+                        base = __shfl_sync(peers, base, leader);
+                        const uint64_t at = base + __popc(peers & ((1u << lane) - 1));
+                        if (at < p.route_cap) p.route_out[owner][at] = h[j];
+                    }
+                }
+            }
+        }
+        if (MODE == kModeCount || MODE == kModeRoute) {
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
+            if ((tid & 31) == 0 && tot) atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
+        }
+        __syncthreads();
+    }
+
+    if (MODE == kModeFirstBad) {
+        for (int o = 16; o; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
+        if ((tid & 31) == 0 && first_bad != ~0ULL)
+            atomicMin((unsigned long long *)&p.table.ctrl->first_bad, (unsigned long long)first_bad);
+    } else if (MODE == kModeCount || MODE == kModeRoute) {
+        for (int o = 16; o; o >>= 1) n_counted += __shfl_xor_sync(0xffffffffu, n_counted, o);
+        if ((tid & 31) == 0 && n_counted)
+            atomicAdd((unsigned long long *)&p.table.ctrl->counted, (unsigned long long)n_counted);
+    }
+}
+
+// ---- any k in 1..255: one window per thread, bytes read from shared memory ----
+__device__ __forceinline__ uint32_t comp1(uint32_t c) { return c ^ ((c & 2) ? 0x04u : 0x15u); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) consume_generic_kernel(const ConsumeParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int K = (int)p.ksize;
+    const int BL = (kTileW + K - 1 + 15) / 16 * 16;
+    const int NV = BL / 16;
+    uint8_t *s_fw = smem;  // the reverse strand is derived on the fly here
+    uint16_t *s_bad = reinterpret_cast<uint16_t *>(smem + BL);
+    uint32_t *s_end = reinterpret_cast<uint32_t *>(smem + BL + ((NV * 2 + 15) / 16 * 16) + 16);
+    const uint32_t *bad32 = reinterpret_cast<const uint32_t *>(s_bad);
+
+    const int tid = threadIdx.x;
+    uint64_t n_counted = 0, first_bad = ~0ULL;
+
+    for (uint64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const uint64_t w0 = p.tile_base + t * kTileW;
+        for (int i = tid; i < BL / 32 + 3; i += kThreads) s_end[i] = 0;
+        if (tid < 8) s_bad[NV + tid] = 0xffff;
+        __syncthreads();
+        for (int v = tid; v < NV; v += kThreads) {
+            // same staging as the specialised kernel, BL known only at run time
+            const uint64_t g = w0 + 16ull * v;
+            uint4 raw = load_bases16(p, g);
+            uint32_t u[4] = {upper4(raw.x), upper4(raw.y), upper4(raw.z), upper4(raw.w)};
+            uint32_t ok = acgt_mask4(u[0]) | (acgt_mask4(u[1]) << 4) | (acgt_mask4(u[2]) << 8) |
+                          (acgt_mask4(u[3]) << 12);
+            if (g + 16 > p.data_end)
+                ok &= g >= p.data_end ? 0u : (0xffffu >> (16 - (uint32_t)(p.data_end - g)));
+            *reinterpret_cast<uint4 *>(s_fw + 16 * v) = make_uint4(u[0], u[1], u[2], u[3]);
+            s_bad[v] = (uint16_t)(~ok);
+        }
+        for (uint64_t r = p.tile_first[t] + tid; r < p.n_off; r += kThreads) {
+            const uint64_t e = p.offsets[r] - 1 - w0;
+            if (e >= (uint64_t)BL) break;
+            atomicOr(&s_end[e >> 5], 1u << (e & 31));
+        }
+        bool full = false;
+        if (MODE == kModeCount) full = __ldcg(&p.table.ctrl->size) >= p.table.limit;
+        __syncthreads();
+
+        uint32_t created = 0;
+        for (int q = tid; q < kTileW; q += kThreads) {
+            const uint64_t gp = w0 + q;
+            const bool in_range = gp >= p.w_lo && gp < p.w_hi;
+            // any bad bit in [q, q+K), any end bit in [q, q+K-1)
+            bool clean = true, in_read = true;
+            for (int b = q; b < q + K; ) {
+                const int word = b >> 5, off = b & 31;
+                const int take = min(32 - off, q + K - b);
+                const uint32_t m = (take == 32 ? ~0u : ((1u << take) - 1)) << off;
+                if (bad32[word] & m) clean = false;
+                const int take_e = min(take, q + K - 1 - b);
+                if (take_e > 0) {
+                    const uint32_t me = (take_e == 32 ? ~0u : ((1u << take_e) - 1)) << off;
+                    if (s_end[word] & me) in_read = false;
+                }
+                b += take;
+            }
+            uint64_t h = 0;
+            if (MODE == kModeFirstBad) {
+                if (in_range && in_read && !clean && gp + K <= p.data_end) first_bad = min(first_bad, gp);
+                continue;
+            }
+            if (in_range && in_read && clean) {
+                bool use_rc = false;
+                for (int i = 0; i < K; ++i) {
+                    const uint32_t a = s_fw[q + i], b = comp1(s_fw[q + K - 1 - i]);
+                    if (a != b) { use_rc = b < a; break; }
+                }
+                h = murmur_bytes(
+                    [&](int i) -> uint64_t {
+                        return use_rc ? comp1(s_fw[q + K - 1 - i]) : (uint32_t)s_fw[q + i];
+                    },
+                    K);
+            }
+            if (MODE == kModeHash) {
+                if (in_range) p.hashes_out[gp - p.w_lo] = h;
+            } else if (MODE == kModeCount) {
+                if (h != 0) { ++n_counted; created += table_add(p.table, h, 1, full); }
+            }
+        }
+        if (MODE == kModeCount) {
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
+            if ((tid & 31) == 0 && tot) atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
+        }
+        __syncthreads();
+    }
+    if (MODE == kModeFirstBad) {
+        for (int o = 16; o; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
+        if ((tid & 31) == 0 && first_bad != ~0ULL)
+            atomicMin((unsigned long long *)&p.table.ctrl->first_bad, (unsigned long long)first_bad);
+    } else if (MODE == kModeCount) {
+        for (int o = 16; o; o >>= 1) n_counted += __shfl_xor_sync(0xffffffffu, n_counted, o);
+        if ((tid & 31) == 0 && n_counted)
+            atomicAdd((unsigned long long *)&p.table.ctrl->counted, (unsigned long long)n_counted);
+    }
+}
+
+}  // namespace oxg
+
+namespace oxg {
+inline size_t generic_smem_bytes(int k) {
+    const int BL = (kTileW + k - 1 + 15) / 16 * 16, NV = BL / 16;
+    return (size_t)BL + ((NV * 2 + 15) / 16 * 16) + 16 + (BL / 32 + 3) * 4;
+}
+}  // namespace oxg

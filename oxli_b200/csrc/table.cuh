@@ -1,0 +1,134 @@
+// table.cuh -- open-addressing u64 -> u64 count table in HBM.
+//
+// Stands in for the reference's `counts: HashMap<u64,u64>`
+// (/root/reference/src/lib.rs:33; entry/insert/get at 100-104, 178, 187, 679).
+// Layout: `cap` (power of two) 16-byte slots {key, count}, linear probing from
+// home(key) = (key * phi64) >> (64 - log2 cap).  An empty slot holds kEmpty as
+// key; that one key value is kept outside the slot array (side_*), so every
+// u64 -- including 0 and 2^64-1 -- is a legal key and 0 a legal count.
+// No tombstones: single-key erase shifts the probe run back, bulk cuts rebuild.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace oxg {
+
+constexpr uint64_t kEmpty = ~0ULL;
+constexpr uint64_t kPhi = 0x9E3779B97F4A7C15ULL;
+constexpr int kMaxProbe = 1024;
+
+struct Ctrl {              // lives in device memory, mirrored to pinned host memory
+    uint64_t size;         // live keys in slots[]
+    uint64_t side_present; // key kEmpty is present
+    uint64_t side_count;   // its count
+    uint64_t counted;      // k-mers counted by the running consume launch
+    uint64_t overflow;     // entries appended to the overflow list
+    uint64_t first_bad;    // error-mode scan: smallest bad window start
+    uint64_t scratch[10];  // per-op outputs (stats, set sizes, ...)
+};
+
+struct TableView {
+    ulonglong2 *slots;
+    uint64_t cap;      // power of two
+    uint32_t shift;    // 64 - log2(cap)
+    uint64_t limit;    // stop creating keys once size reaches this
+    Ctrl *ctrl;
+    uint64_t *overflow;   // deferred hashes (table too full), may be null
+    uint64_t overflow_cap;
+    __device__ __forceinline__ uint64_t home(uint64_t key) const {
+        return shift >= 64 ? 0 : (key * kPhi) >> shift;
+    }
+};
+
+__device__ __forceinline__ void red_add64(unsigned long long *p, uint64_t v) {
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ ulonglong2 load_slot(const ulonglong2 *p) { return __ldcg(p); }
+
+__device__ __forceinline__ void push_overflow(const TableView &t, uint64_t key) {
+    uint64_t at = atomicAdd((unsigned long long *)&t.ctrl->overflow, 1ULL);
+    if (t.overflow && at < t.overflow_cap) t.overflow[at] = key;
+}
+
+// counts[key] += inc.  `full` = do not create keys (the table reached its load
+// limit): misses are deferred to the overflow list and replayed after growth.
+// Returns 1 when a new key was created.
+__device__ __forceinline__ uint32_t table_add(const TableView &t, uint64_t key, uint64_t inc,
+                                              bool full) {
+    if (key == kEmpty) {
+        atomicAdd((unsigned long long *)&t.ctrl->side_count, (unsigned long long)inc);
+        t.ctrl->side_present = 1;
+        return 0;
+    }
+    uint64_t i = t.home(key);
+    for (int probe = 0; probe < kMaxProbe; ++probe) {
+        ulonglong2 s = load_slot(t.slots + i);
+        if (s.x == key) {
+            red_add64(&t.slots[i].y, inc);
+            return 0;
+        }
+        if (s.x == kEmpty) {
+            if (full) break;
+            uint64_t old = atomicCAS((unsigned long long *)&t.slots[i].x, kEmpty, key);
+            if (old == kEmpty) {
+                red_add64(&t.slots[i].y, inc);
+                return 1;
+            }
+            if (old == key) {
+                red_add64(&t.slots[i].y, inc);
+                return 0;
+            }
+        }
+        i = (i + 1) & (t.cap - 1);
+    }
+    push_overflow(t, key);
+    return 0;
+}
+
+// same, but returns the count after the increment (count_hash, src/lib.rs:100-104);
+// never defers: the caller reserved room.
+__device__ __forceinline__ uint64_t table_add_fetch(const TableView &t, uint64_t key, uint64_t inc,
+                                                    uint32_t *created) {
+    if (key == kEmpty) {
+        t.ctrl->side_present = 1;
+        return atomicAdd((unsigned long long *)&t.ctrl->side_count, (unsigned long long)inc) + inc;
+    }
+    uint64_t i = t.home(key);
+    for (;;) {
+        ulonglong2 s = load_slot(t.slots + i);
+        if (s.x == kEmpty) {
+            uint64_t old = atomicCAS((unsigned long long *)&t.slots[i].x, kEmpty, key);
+            if (old == kEmpty) { *created += 1; s.x = key; }
+            else s.x = old;
+        }
+        if (s.x == key)
+            return atomicAdd((unsigned long long *)&t.slots[i].y, (unsigned long long)inc) + inc;
+        i = (i + 1) & (t.cap - 1);
+    }
+}
+
+// slot index of key, or -1
+__device__ __forceinline__ int64_t table_find(const TableView &t, uint64_t key) {
+    uint64_t i = t.home(key);
+    for (uint64_t probe = 0; probe < t.cap; ++probe) {
+        ulonglong2 s = load_slot(t.slots + i);
+        if (s.x == key) return (int64_t)i;
+        if (s.x == kEmpty) return -1;
+        i = (i + 1) & (t.cap - 1);
+    }
+    return -1;
+}
+
+__device__ __forceinline__ bool table_contains(const TableView &t, uint64_t key) {
+    if (key == kEmpty) return t.ctrl->side_present != 0;
+    return table_find(t, key) >= 0;
+}
+
+__device__ __forceinline__ uint64_t table_get(const TableView &t, uint64_t key) {
+    if (key == kEmpty) return t.ctrl->side_present ? t.ctrl->side_count : 0;
+    int64_t i = table_find(t, key);
+    return i < 0 ? 0 : __ldcg(&t.slots[i].y);
+}
+
+}  // namespace oxg
