@@ -180,6 +180,9 @@ oxg_status oxg_memcpy_h2d(int device, void *d_dst, const void *src, uint64_t byt
 oxg_status oxg_memcpy_d2h(int device, void *dst, const void *d_src, uint64_t bytes);
 /* block until everything queued for this table's GPU has finished */
 oxg_status oxg_sync(oxg_table *t);
+/* CUDA-event stopwatch on the stream this table's kernels are launched on */
+oxg_status oxg_timer_start(oxg_table *t);
+oxg_status oxg_timer_stop(oxg_table *t, float *ms);
 /* kernels launched by this library in this process so far (bench bookkeeping) */
 uint64_t oxg_launch_count(void);
 /* device-time of the consume kernels of the last oxg_consume_* call on `t`, in

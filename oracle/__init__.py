@@ -165,6 +165,9 @@ class OracleTable:
     def set_hash(self, h, v):
         lib().oxo_table_set_hash(self._t, h, v)
 
+    def contains(self, h) -> bool:
+        return bool(lib().oxo_table_contains(self._t, h))
+
     def drop_hash(self, h):
         lib().oxo_table_drop_hash(self._t, h)
 

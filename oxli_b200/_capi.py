@@ -76,6 +76,8 @@ SIGNATURES = {
     "oxg_memcpy_h2d": (C.c_int, [C.c_int, vp, vp, u64]),
     "oxg_memcpy_d2h": (C.c_int, [C.c_int, vp, vp, u64]),
     "oxg_sync": (C.c_int, [vp]),
+    "oxg_timer_start": (C.c_int, [vp]),
+    "oxg_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "oxg_launch_count": (u64, []),
     "oxg_last_consume_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float), u64p]),
 }
@@ -259,6 +261,14 @@ class Table:
 
     def sync(self):
         check(lib.oxg_sync(self._h))
+
+    def timer_start(self):
+        check(lib.oxg_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        check(lib.oxg_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def last_consume_kernel_ms(self) -> tuple[float, int]:
         ms, n = C.c_float(), u64()

@@ -71,6 +71,7 @@ struct DeviceCtx {
     uint64_t offs_cap[2] = {0, 0};
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_user0 = nullptr, ev_user1 = nullptr;
     // scratch
     uint64_t *d_tile_first = nullptr; uint64_t tile_first_cap = 0;
     uint64_t *d_overflow = nullptr;   uint64_t overflow_cap = 0;
@@ -111,6 +112,8 @@ oxg_status get_ctx(int dev, DeviceCtx **out) {
         }
         CU(cudaEventCreate(&c->ev_t0));
         CU(cudaEventCreate(&c->ev_t1));
+        CU(cudaEventCreate(&c->ev_user0));
+        CU(cudaEventCreate(&c->ev_user1));
         CU(cudaMalloc(&c->d_dense, kHistDense * sizeof(uint64_t)));
         CU(cudaMalloc(&c->d_f64, 4 * sizeof(double)));
         g_ctx[dev] = std::move(c);
@@ -447,6 +450,21 @@ oxg_status oxg_sync(oxg_table *t) {
     ENTER(t);
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->copy));
+    return OXG_OK;
+}
+
+oxg_status oxg_timer_start(oxg_table *t) {
+    ENTER(t);
+    CU(cudaEventRecord(c->ev_user0, c->stream));
+    return OXG_OK;
+}
+
+oxg_status oxg_timer_stop(oxg_table *t, float *ms) {
+    ENTER(t);
+    if (!ms) return fail(OXG_ERR_INVALID, "null argument");
+    CU(cudaEventRecord(c->ev_user1, c->stream));
+    CU(cudaEventSynchronize(c->ev_user1));
+    CU(cudaEventElapsedTime(ms, c->ev_user0, c->ev_user1));
     return OXG_OK;
 }
 

@@ -62,7 +62,8 @@ __device__ __forceinline__ uint32_t table_add(const TableView &t, uint64_t key, 
         return 0;
     }
     uint64_t i = t.home(key);
-    for (int probe = 0; probe < kMaxProbe; ++probe) {
+    // only launches that carry a deferral list may give up on a long probe run
+    for (int probe = 0; t.overflow == nullptr || probe < kMaxProbe; ++probe) {
         ulonglong2 s = load_slot(t.slots + i);
         if (s.x == key) {
             red_add64(&t.slots[i].y, inc);

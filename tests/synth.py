@@ -25,6 +25,10 @@ def genome_base(seed: int, pos: np.ndarray) -> np.ndarray:
 def synth_reads(n_reads: int, read_len: int, genome_len: int, seed: int, first_read: int = 0,
                 sub_ppm: int = 0, n_ppm: int = 0) -> np.ndarray:
     """uint8 array of n_reads*read_len ASCII bases, identical to oxg_synth_reads_device."""
+    step = 100_000
+    if n_reads > step:  # bound the temporaries
+        return np.concatenate([synth_reads(min(step, n_reads - a), read_len, genome_len, seed, first_read + a,
+                                           sub_ppm, n_ppm) for a in range(0, n_reads, step)])
     r = np.arange(n_reads, dtype=np.uint64)
     with np.errstate(over="ignore"):
         rk = splitmix64((np.uint64(seed) ^ np.uint64(0x5EEDF00D)) + (np.uint64(first_read) + r) * np.uint64(0x2545F4914F6CDD1D))
