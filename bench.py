@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-reads", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--table-hint", type=int, default=0, help="expected distinct k-mers (default: genome length)")
     return ap.parse_args()
 
 
@@ -122,7 +123,7 @@ def run_reference(a, rank, world):
     if rank != 0:
         return
     import oracle
-    from tests.synth import synth_reads, uniform_offsets
+    from oracle.synth import synth_reads, uniform_offsets
 
     cores = os.cpu_count() or 1
     n = min(a.reads, max(a.cpu_sample_reads, 50_000 * cores))
@@ -153,7 +154,7 @@ def run_reference(a, rank, world):
 
 def cpu_baseline(a, capi, d_bases) -> dict:
     import oracle
-    from tests.synth import uniform_offsets
+    from oracle.synth import uniform_offsets
 
     n = min(a.reads, a.cpu_sample_reads)
     bases = np.empty(n * a.read_len, dtype=np.uint8)
@@ -191,7 +192,7 @@ def main():
     capi.synth_reads_device(d_bases, n, L, a.genome, SEED, device=dev)
     offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
     capi.h2d(d_offs, offs, dev)
-    table = capi.Table(k, device=dev, capacity_hint=a.genome)
+    table = capi.Table(k, device=dev, capacity_hint=a.table_hint or a.genome)
 
     def step_resident():
         table.clear()

@@ -179,7 +179,7 @@ TableView view_of(const oxg_table *t, bool with_overflow) {
     uint32_t lg = 0;
     while ((1ull << lg) < t->cap) ++lg;
     v.shift = 64 - lg;
-    v.limit = t->cap - t->cap / 4;  // stop creating keys at 75 % load
+    v.limit = t->cap - t->cap / 5;  // stop creating keys at 80 % load
     v.ctrl = t->d_ctrl;
     v.overflow = with_overflow ? t->ctx->d_overflow : nullptr;
     v.overflow_cap = with_overflow ? t->ctx->overflow_cap : 0;
@@ -200,6 +200,7 @@ oxg_status zero_ctrl_fields(oxg_table *t, size_t first_field, size_t n_fields) {
     return OXG_OK;
 }
 constexpr size_t kFieldCounted = offsetof(Ctrl, counted) / 8;
+constexpr size_t kFieldTile = offsetof(Ctrl, tile_counter) / 8;
 constexpr size_t kFieldScratch = offsetof(Ctrl, scratch) / 8;
 
 oxg_status alloc_slots(DeviceCtx *c, uint64_t cap, ulonglong2 **out) {
@@ -237,12 +238,15 @@ template <int MODE>
 oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
     DeviceCtx *c = t->ctx;
     const int k = (int)t->k;
-    int grid = (int)std::min<uint64_t>(p.n_tiles, (uint64_t)c->sms * 8);
-    if (grid < 1) grid = 1;
+    auto grid_of = [&](const void *fn, size_t smem) {
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        return (int)std::max<uint64_t>(1, std::min<uint64_t>(p.n_tiles, (uint64_t)c->sms * per_sm));
+    };
     switch (k) {
-#define OXG_CASE(KK)                                                                    \
-    case KK:                                                                            \
-        consume_kernel<KK, MODE><<<grid, kThreads, 0, c->stream>>>(p);                  \
+#define OXG_CASE(KK)                                                                              \
+    case KK:                                                                                      \
+        consume_kernel<KK, MODE><<<grid_of((const void *)consume_kernel<KK, MODE>, 0), kThreads, 0, c->stream>>>(p); \
         break;
         OXG_CASE(21)
         OXG_CASE(31)
@@ -251,7 +255,7 @@ oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
         if (MODE == kModeRoute) return fail(OXG_ERR_INVALID, "sharded routing is built for k = 21 and 31 only");
         if constexpr (MODE != kModeRoute) {
             const size_t smem = generic_smem_bytes(k);
-            consume_generic_kernel<MODE><<<grid, kThreads, smem, c->stream>>>(p);
+            consume_generic_kernel<MODE><<<grid_of((const void *)consume_generic_kernel<MODE>, smem), kThreads, smem, c->stream>>>(p);
         }
     }
     LAUNCHED();
@@ -279,9 +283,11 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
         if (mode == kModeCount) {
             const uint64_t span = hi - lo;
             if (span <= kSmallBatch) TRY(reserve_keys(t, span));
-            else if (t->size * 2 > t->cap) TRY(grow_to_fit(t, t->size * 2));
+            else if (t->size * 10 > t->cap * 7) TRY(grow_to_fit(t, t->size));  // > 70 % load: double
             TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, span));
-            TRY(zero_ctrl_fields(t, kFieldCounted, 2));  // counted, overflow
+            TRY(zero_ctrl_fields(t, kFieldCounted, 3));  // counted, overflow, tile_counter
+        } else {
+            TRY(zero_ctrl_fields(t, kFieldTile, 1));
         }
         ConsumeParams p{};
         p.bases = d_bases; p.g0 = g0; p.w_lo = lo; p.w_hi = hi; p.data_end = data_end;
@@ -1043,9 +1049,9 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
         const uint64_t hi = std::min(n_win, lo + kLaunchWindows);
         const uint64_t n_tiles = (hi - lo + kTileW - 1) / kTileW;
         TRY(ensure_dev(&c->d_tile_first, &c->tile_first_cap, n_tiles));
-        if (t->size * 2 > t->cap) TRY(grow_to_fit(t, t->size * 2));
+        if (t->size * 10 > t->cap * 7) TRY(grow_to_fit(t, t->size));
         TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, hi - lo));
-        TRY(zero_ctrl_fields(t, kFieldCounted, 2));
+        TRY(zero_ctrl_fields(t, kFieldCounted, 3));
         ConsumeParams p{};
         p.bases = d_bases; p.g0 = 0; p.w_lo = lo; p.w_hi = hi; p.data_end = total_bases;
         p.tile_base = lo; p.n_tiles = n_tiles; p.offsets = d_offsets; p.n_off = n_reads + 1;

@@ -118,31 +118,86 @@ __device__ __forceinline__ void stage16(const ConsumeParams &p, uint64_t w0, int
     s_bad[v] = (uint16_t)(~ok);
 }
 
+// Count up to kWPT hashes per thread (0 = nothing to count).  Fast path: one
+// 256-bit load fetches the key's home bucket (two 16-byte slots = one 32-byte
+// sector); a hit in either slot is one RED.  Everything else (displaced keys,
+// new keys, table at its load limit) is compacted into a per-warp shared-memory
+// queue and drained with all lanes busy, so the rare long probe does not leave
+// the warp one-lane-wide.
+__device__ __forceinline__ void count_hashes8(const TableView &tv, const uint64_t (&h)[kWPT], bool full,
+                                              uint64_t *s_queue /* this warp's kWPT*32 entries */,
+                                              uint64_t &n_counted, uint32_t &created) {
+    const int lane = threadIdx.x & 31;
+    uint32_t pending = 0;
+#pragma unroll
+    for (int half = 0; half < kWPT / 4; ++half) {
+        uint64_t idx[4];
+        ulonglong2 a[4], b[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = half * 4 + q;
+            idx[q] = tv.home(h[j]);
+            if (h[j] != 0) load_pair(tv.slots + idx[q], a[q], b[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int j = half * 4 + q;
+            if (h[j] == 0) continue;  // bad window, or the reference's hash==0 skip (src/lib.rs:589)
+            ++n_counted;
+            if (a[q].x == h[j]) red_add64(&tv.slots[idx[q]].y, 1);
+            else if (b[q].x == h[j]) red_add64(&tv.slots[idx[q] + 1].y, 1);
+            else pending |= 1u << j;
+        }
+    }
+    uint32_t qn = 0;  // warp-uniform
+#pragma unroll
+    for (int j = 0; j < kWPT; ++j) {
+        const bool mine = (pending >> j) & 1u;
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        if (mine) s_queue[qn + __popc(m & ((1u << lane) - 1))] = h[j];
+        qn += __popc(m);
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < qn; i += 32) created += table_add(tv, s_queue[i], 1, full);
+    __syncwarp();
+}
+
 template <int K, int MODE>
-__global__ void __launch_bounds__(kThreads) consume_kernel(const ConsumeParams p) {
+__global__ void __launch_bounds__(kThreads, 3) consume_kernel(const ConsumeParams p) {
     static_assert(K >= 1 && K <= 32, "specialised kernel covers k <= 32");
     constexpr int Q = 8 * ((K + 7 + 7) / 8);  // bytes a thread pulls per strand
     constexpr int BL = ((kTileW - 8 + Q) + 15) / 16 * 16;
     constexpr int NV = BL / 16;
     constexpr int NX = Q / 8;
     constexpr int NW = (K + 7) / 8;
-    constexpr uint64_t MK = K == 64 ? ~0ULL : ((1ULL << K) - 1);
+    constexpr uint64_t MK = (K == 64) ? ~0ULL : ((1ULL << K) - 1);
     constexpr uint64_t MK1 = (1ULL << (K - 1)) - 1;
     constexpr uint64_t TAILMASK = (K % 8) ? (~0ULL >> (8 * (8 - K % 8))) : ~0ULL;
+    constexpr bool kCounts = MODE == kModeCount || MODE == kModeRoute;
 
     __shared__ __align__(16) uint8_t s_fw[BL];
     __shared__ __align__(16) uint8_t s_rc[BL];
     __shared__ __align__(8) uint16_t s_bad[NV + 6];
-    __shared__ __align__(8) uint32_t s_end[BL / 32 + 3];
+    constexpr int NE = BL / 32 + 3;
+    __shared__ __align__(8) uint32_t s_end2[2][NE + (NE & 1)];  // alternates per tile, see below
+    __shared__ __align__(8) uint64_t s_queue[kCounts ? kThreads * kWPT : 1];
+    __shared__ uint64_t s_tile;
 
     const int tid = threadIdx.x;
     uint64_t n_counted = 0;
     uint64_t first_bad = ~0ULL;
 
-    for (uint64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const uint64_t w0 = p.tile_base + t * kTileW;
-        for (int i = tid; i < BL / 32 + 3; i += kThreads) s_end[i] = 0;
+    for (uint32_t it = 0;; ++it) {
+        // Tiles are handed out dynamically: the grid is sized to what is resident.
+        // Two barriers per tile: slow warps may still be reading the previous tile's
+        // end-mask while fast ones clear the next one, hence the two copies.
+        uint32_t *s_end = s_end2[it & 1];
+        if (tid == 0) s_tile = atomicAdd((unsigned long long *)&p.table.ctrl->tile_counter, 1ULL);
+        for (int i = tid; i < NE; i += kThreads) s_end[i] = 0;
         __syncthreads();
+        const uint64_t t = s_tile;
+        if (t >= p.n_tiles) break;
+        const uint64_t w0 = p.tile_base + t * kTileW;
 
         if (tid < NV) stage16<BL>(p, w0, tid, s_fw, s_rc, s_bad);
         for (uint64_t r = p.tile_first[t] + tid; r < p.n_off; r += kThreads) {
@@ -151,8 +206,7 @@ __global__ void __launch_bounds__(kThreads) consume_kernel(const ConsumeParams p
             atomicOr(&s_end[e >> 5], 1u << (e & 31));
         }
         bool full = false;
-        if (MODE == kModeCount || MODE == kModeRoute)
-            full = __ldcg(&p.table.ctrl->size) >= p.table.limit;
+        if (kCounts) full = __ldcg(&p.table.ctrl->size) >= p.table.limit;
         __syncthreads();
 
         const int p0 = tid * kWPT;
@@ -175,77 +229,59 @@ __global__ void __launch_bounds__(kThreads) consume_kernel(const ConsumeParams p
                 valid |= 1u << j;
             }
         }
+        if (MODE == kModeFirstBad) continue;
 
-        uint32_t created = 0;
-        if (MODE != kModeFirstBad) {
-            uint64_t h[kWPT];
+        uint64_t h[kWPT] = {};
+        if (valid) {
+            uint64_t F[NX], R[NX];
+            const uint64_t *f64 = reinterpret_cast<const uint64_t *>(s_fw + p0);
+            const uint64_t *r64 = reinterpret_cast<const uint64_t *>(s_rc + BL - p0 - Q);
 #pragma unroll
-            for (int j = 0; j < kWPT; ++j) h[j] = 0;
-            if (valid) {
-                uint64_t F[NX], R[NX];
-                const uint64_t *f64 = reinterpret_cast<const uint64_t *>(s_fw + p0);
-                const uint64_t *r64 = reinterpret_cast<const uint64_t *>(s_rc + BL - p0 - Q);
-#pragma unroll
-                for (int i = 0; i < NX; ++i) { F[i] = f64[i]; R[i] = r64[i]; }
+            for (int i = 0; i < NX; ++i) { F[i] = f64[i]; R[i] = r64[i]; }
 
-                auto hash_one = [&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    constexpr int FO = j, RO = Q - K - j;
-                    uint64_t a[NW], b[NW];
-                    static_for<NW>([&](auto ic) {
-                        constexpr int i = decltype(ic)::value;
-                        a[i] = word_at<FO + 8 * i>(F);
-                        b[i] = word_at<RO + 8 * i>(R);
-                    });
-                    a[NW - 1] &= TAILMASK;
-                    b[NW - 1] &= TAILMASK;
-                    bool use_rc = bswap64(b[0]) < bswap64(a[0]);
-                    if (NW > 1 && a[0] == b[0]) {  // rare: first 8 bases tie
+            auto hash_one = [&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                constexpr int FO = j, RO = Q - K - j;
+                uint64_t a[NW], b[NW];
+                static_for<NW>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    a[i] = word_at<FO + 8 * i>(F);
+                    b[i] = word_at<RO + 8 * i>(R);
+                });
+                a[NW - 1] &= TAILMASK;
+                b[NW - 1] &= TAILMASK;
+                bool use_rc = bswap64(b[0]) < bswap64(a[0]);
+                if (NW > 1 && a[0] == b[0]) {  // rare: first 8 bases tie
 #pragma unroll
-                        for (int i = 1; i < NW; ++i) {
-                            if (a[i] != b[i]) { use_rc = bswap64(b[i]) < bswap64(a[i]); break; }
-                        }
+                    for (int i = 1; i < NW; ++i) {
+                        if (a[i] != b[i]) { use_rc = bswap64(b[i]) < bswap64(a[i]); break; }
                     }
-                    uint64_t w[NW];
-#pragma unroll
-                    for (int i = 0; i < NW; ++i) w[i] = use_rc ? b[i] : a[i];
-                    h[j] = ((valid >> j) & 1u) ? murmur_words<K>(w) : 0;
-                };
-                static_for<kWPT>(hash_one);
-            }
-
-            if (MODE == kModeHash) {
-#pragma unroll
-                for (int j = 0; j < kWPT; ++j)
-                    if (gp0 + j >= p.w_lo && gp0 + j < p.w_hi) p.hashes_out[gp0 + j - p.w_lo] = h[j];
-            } else if (MODE == kModeCount) {
-                // issue all home-slot loads first (memory-level parallelism), then resolve
-                uint64_t idx[kWPT];
-                ulonglong2 s[kWPT];
-#pragma unroll
-                for (int j = 0; j < kWPT; ++j) idx[j] = p.table.home(h[j]);
-#pragma unroll
-                for (int j = 0; j < kWPT; ++j)
-                    if (h[j] != 0) s[j] = load_slot(p.table.slots + idx[j]);
-#pragma unroll
-                for (int j = 0; j < kWPT; ++j) {
-                    if (h[j] == 0) continue;  // bad window, or the reference's hash==0 skip
-                    ++n_counted;
-                    if (s[j].x == h[j]) red_add64(&p.table.slots[idx[j]].y, 1);
-                    else created += table_add(p.table, h[j], 1, full);
                 }
-            } else if (MODE == kModeRoute) {
+                uint64_t w[NW];
+#pragma unroll
+                for (int i = 0; i < NW; ++i) w[i] = use_rc ? b[i] : a[i];
+                h[j] = ((valid >> j) & 1u) ? murmur_words<K>(w) : 0;
+            };
+            static_for<kWPT>(hash_one);
+        }
+
+        if (MODE == kModeHash) {
+#pragma unroll
+            for (int j = 0; j < kWPT; ++j)
+                if (gp0 + j >= p.w_lo && gp0 + j < p.w_hi) p.hashes_out[gp0 + j - p.w_lo] = h[j];
+        } else if (kCounts) {
+            uint32_t created = 0;
+            if (MODE == kModeRoute) {
+                // hashes owned elsewhere go to the owner's outgoing list (warp-aggregated append)
+                const int lane = tid & 31;
 #pragma unroll
                 for (int j = 0; j < kWPT; ++j) {
-                    if (h[j] == 0) continue;
                     const int owner = (int)(h[j] >> p.owner_shift);
-                    if (owner == p.self_rank) {
-                        ++n_counted;
-                        created += table_add(p.table, h[j], 1, full);
-                    } else {
-                        // warp-aggregated append to the owner's outgoing list
-                        const unsigned peers = __match_any_sync(__activemask(), owner);
-                        const int leader = __ffs(peers) - 1, lane = tid & 31;
+                    const bool remote = h[j] != 0 && owner != p.self_rank;
+                    const unsigned rm = __ballot_sync(0xffffffffu, remote);
+                    if (remote) {
+                        const unsigned peers = __match_any_sync(rm, owner);
+                        const int leader = __ffs(peers) - 1;
                         uint64_t base = 0;
                         if (lane == leader)
                             base = atomicAdd((unsigned long long *)&p.route_counts[owner],
@@ -253,22 +289,21 @@ __global__ void __launch_bounds__(kThreads) consume_kernel(const ConsumeParams p
                         base = __shfl_sync(peers, base, leader);
                         const uint64_t at = base + __popc(peers & ((1u << lane) - 1));
                         if (at < p.route_cap) p.route_out[owner][at] = h[j];
+                        h[j] = 0;
                     }
                 }
             }
-        }
-        if (MODE == kModeCount || MODE == kModeRoute) {
+            count_hashes8(p.table, h, full, s_queue + (tid >> 5) * (kWPT * 32), n_counted, created);
             const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
             if ((tid & 31) == 0 && tot) atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
         }
-        __syncthreads();
     }
 
     if (MODE == kModeFirstBad) {
         for (int o = 16; o; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
         if ((tid & 31) == 0 && first_bad != ~0ULL)
             atomicMin((unsigned long long *)&p.table.ctrl->first_bad, (unsigned long long)first_bad);
-    } else if (MODE == kModeCount || MODE == kModeRoute) {
+    } else if (kCounts) {
         for (int o = 16; o; o >>= 1) n_counted += __shfl_xor_sync(0xffffffffu, n_counted, o);
         if ((tid & 31) == 0 && n_counted)
             atomicAdd((unsigned long long *)&p.table.ctrl->counted, (unsigned long long)n_counted);
@@ -292,11 +327,15 @@ __global__ void __launch_bounds__(kThreads) consume_generic_kernel(const Consume
     const int tid = threadIdx.x;
     uint64_t n_counted = 0, first_bad = ~0ULL;
 
-    for (uint64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const uint64_t w0 = p.tile_base + t * kTileW;
+    __shared__ uint64_t s_tile;
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd((unsigned long long *)&p.table.ctrl->tile_counter, 1ULL);
         for (int i = tid; i < BL / 32 + 3; i += kThreads) s_end[i] = 0;
         if (tid < 8) s_bad[NV + tid] = 0xffff;
         __syncthreads();
+        const uint64_t t = s_tile;
+        if (t >= p.n_tiles) break;
+        const uint64_t w0 = p.tile_base + t * kTileW;
         for (int v = tid; v < NV; v += kThreads) {
             // same staging as the specialised kernel, BL known only at run time
             const uint64_t g = w0 + 16ull * v;

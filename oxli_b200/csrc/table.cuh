@@ -3,7 +3,8 @@
 // Stands in for the reference's `counts: HashMap<u64,u64>`
 // (/root/reference/src/lib.rs:33; entry/insert/get at 100-104, 178, 187, 679).
 // Layout: `cap` (power of two) 16-byte slots {key, count}, linear probing from
-// home(key) = (key * phi64) >> (64 - log2 cap).  An empty slot holds kEmpty as
+// home(key) = ((key * phi64) >> (64 - log2 cap)) & ~1, i.e. from the first slot of
+// a 32-byte, two-slot bucket.  An empty slot holds kEmpty as
 // key; that one key value is kept outside the slot array (side_*), so every
 // u64 -- including 0 and 2^64-1 -- is a legal key and 0 a legal count.
 // No tombstones: single-key erase shifts the probe run back, bulk cuts rebuild.
@@ -23,6 +24,7 @@ struct Ctrl {              // lives in device memory, mirrored to pinned host me
     uint64_t side_count;   // its count
     uint64_t counted;      // k-mers counted by the running consume launch
     uint64_t overflow;     // entries appended to the overflow list
+    uint64_t tile_counter; // dynamic tile scheduler of the running consume launch
     uint64_t first_bad;    // error-mode scan: smallest bad window start
     uint64_t scratch[10];  // per-op outputs (stats, set sizes, ...)
 };
@@ -35,8 +37,9 @@ struct TableView {
     Ctrl *ctrl;
     uint64_t *overflow;   // deferred hashes (table too full), may be null
     uint64_t overflow_cap;
+    // home slot: even, so a key's first two candidate slots share one 32-byte sector
     __device__ __forceinline__ uint64_t home(uint64_t key) const {
-        return shift >= 64 ? 0 : (key * kPhi) >> shift;
+        return ((key * kPhi) >> shift) & ~1ULL;
     }
 };
 
@@ -45,6 +48,13 @@ __device__ __forceinline__ void red_add64(unsigned long long *p, uint64_t v) {
 }
 
 __device__ __forceinline__ ulonglong2 load_slot(const ulonglong2 *p) { return __ldcg(p); }
+
+// both slots of a home bucket with one 256-bit load (sm_100: LDG.E.256)
+__device__ __forceinline__ void load_pair(const ulonglong2 *p, ulonglong2 &a, ulonglong2 &b) {
+    asm("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+        : "=l"(a.x), "=l"(a.y), "=l"(b.x), "=l"(b.y)
+        : "l"(p));
+}
 
 __device__ __forceinline__ void push_overflow(const TableView &t, uint64_t key) {
     uint64_t at = atomicAdd((unsigned long long *)&t.ctrl->overflow, 1ULL);
