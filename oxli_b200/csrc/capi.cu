@@ -234,6 +234,9 @@ oxg_status grow_to_fit(oxg_table *t, uint64_t keys) {
 
 oxg_status reserve_keys(oxg_table *t, uint64_t extra) { return grow_to_fit(t, t->size + extra); }
 
+bool specialised_k(uint32_t k) { return k == 21 || k == 31; }
+uint32_t tile_width(uint32_t k) { return specialised_k(k) ? kWarpTile : kTileW; }
+
 template <int MODE>
 oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
     DeviceCtx *c = t->ctx;
@@ -241,7 +244,8 @@ oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
     auto grid_of = [&](const void *fn, size_t smem) {
         int per_sm = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-        return (int)std::max<uint64_t>(1, std::min<uint64_t>(p.n_tiles, (uint64_t)c->sms * per_sm));
+        const uint64_t tiles_per_cta = specialised_k(t->k) ? kThreads / 32 : 1;
+        return (int)std::max<uint64_t>(1, std::min<uint64_t>((p.n_tiles + tiles_per_cta - 1) / tiles_per_cta, (uint64_t)c->sms * per_sm));
     };
     switch (k) {
 #define OXG_CASE(KK)                                                                              \
@@ -278,7 +282,8 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
     while (lo < w_hi) {
         const uint64_t tile_base = std::max<uint64_t>(g0, lo & ~(uint64_t)15);
         uint64_t hi = std::min<uint64_t>(w_hi, tile_base + kLaunchWindows);
-        const uint64_t n_tiles = (hi - tile_base + kTileW - 1) / kTileW;
+        const uint32_t tw = tile_width(t->k);
+        const uint64_t n_tiles = (hi - tile_base + tw - 1) / tw;
         TRY(ensure_dev(&c->d_tile_first, &c->tile_first_cap, n_tiles));
         if (mode == kModeCount) {
             const uint64_t span = hi - lo;
@@ -294,7 +299,7 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
         p.tile_base = tile_base; p.n_tiles = n_tiles; p.offsets = d_offsets; p.n_off = n_off;
         p.tile_first = c->d_tile_first; p.table = view_of(t, mode == kModeCount);
         p.hashes_out = hashes_out ? hashes_out + (lo - w_lo) : nullptr; p.ksize = t->k;
-        tile_first_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(d_offsets, n_off, tile_base, n_tiles, c->d_tile_first);
+        tile_first_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(d_offsets, n_off, tile_base, n_tiles, tw, c->d_tile_first);
         LAUNCHED();
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->ev_t0, c->stream));
@@ -1047,7 +1052,8 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
     uint64_t lo = 0;
     while (lo < n_win) {
         const uint64_t hi = std::min(n_win, lo + kLaunchWindows);
-        const uint64_t n_tiles = (hi - lo + kTileW - 1) / kTileW;
+        const uint32_t tw = tile_width(t->k);
+        const uint64_t n_tiles = (hi - lo + tw - 1) / tw;
         TRY(ensure_dev(&c->d_tile_first, &c->tile_first_cap, n_tiles));
         if (t->size * 10 > t->cap * 7) TRY(grow_to_fit(t, t->size));
         TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, hi - lo));
@@ -1061,7 +1067,7 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
         for (int r = 0; r < n_ranks; ++r) p.route_out[r] = d_out ? d_out[r] : nullptr;
         p.route_counts = d_out_counts; p.route_cap = out_cap;
         if (lg == 0) return fail(OXG_ERR_INVALID, "use oxg_consume_batch_device when n_ranks == 1");
-        tile_first_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(d_offsets, n_reads + 1, lo, n_tiles, c->d_tile_first);
+        tile_first_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(d_offsets, n_reads + 1, lo, n_tiles, tw, c->d_tile_first);
         LAUNCHED();
         CU(cudaEventRecord(c->ev_t0, c->stream));
         TRY(launch_consume<kModeRoute>(t, p));

@@ -39,6 +39,7 @@ constexpr int kTileW = 2048;  // window starts per tile
 constexpr int kThreads = 256;
 constexpr int kWPT = kTileW / kThreads;  // 8 consecutive windows per thread
 static_assert(kWPT == 8, "bit-mask extraction assumes 8 windows per thread");
+constexpr int kWarpTile = 32 * kWPT;  // window starts per warp tile in the specialised kernel
 constexpr int kMaxRanks = 16;
 
 enum Mode : int {
@@ -70,11 +71,11 @@ struct ConsumeParams {
 };
 
 __global__ void tile_first_kernel(const uint64_t *__restrict__ offsets, uint64_t n_off,
-                                  uint64_t tile_base, uint64_t n_tiles,
+                                  uint64_t tile_base, uint64_t n_tiles, uint32_t tile_w,
                                   uint64_t *__restrict__ tile_first) {
     uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    const uint64_t want = tile_base + t * kTileW + 1;  // first offsets[r] >= want
+    const uint64_t want = tile_base + t * tile_w + 1;  // first offsets[r] >= want
     uint64_t lo = 0, hi = n_off;
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;
@@ -128,7 +129,7 @@ __device__ __forceinline__ void count_hashes8(const TableView &tv, const uint64_
                                               uint64_t *s_queue /* this warp's kWPT*32 entries */,
                                               uint64_t &n_counted, uint32_t &created) {
     const int lane = threadIdx.x & 31;
-    uint32_t pending = 0;
+    uint32_t pending = 0, restart = 0;
 #pragma unroll
     for (int half = 0; half < kWPT / 4; ++half) {
         uint64_t idx[4];
@@ -146,70 +147,91 @@ __device__ __forceinline__ void count_hashes8(const TableView &tv, const uint64_
             ++n_counted;
             if (a[q].x == h[j]) red_add64(&tv.slots[idx[q]].y, 1);
             else if (b[q].x == h[j]) red_add64(&tv.slots[idx[q] + 1].y, 1);
-            else pending |= 1u << j;
+            else {
+                pending |= 1u << j;
+                // an empty slot in the home bucket means "maybe insert here": redo that bucket
+                if (a[q].x == kEmpty || b[q].x == kEmpty) restart |= 1u << j;
+            }
         }
     }
+    // queue entry: the key, plus a companion byte telling where to resume probing
+    uint64_t *s_key = s_queue;
+    uint8_t *s_skip = reinterpret_cast<uint8_t *>(s_queue + kWPT * 32);
     uint32_t qn = 0;  // warp-uniform
 #pragma unroll
     for (int j = 0; j < kWPT; ++j) {
         const bool mine = (pending >> j) & 1u;
         const unsigned m = __ballot_sync(0xffffffffu, mine);
-        if (mine) s_queue[qn + __popc(m & ((1u << lane) - 1))] = h[j];
+        if (mine) {
+            const uint32_t at = qn + __popc(m & ((1u << lane) - 1));
+            s_key[at] = h[j];
+            s_skip[at] = ((restart >> j) & 1u) ? 0 : 2;
+        }
         qn += __popc(m);
     }
     __syncwarp();
-    for (uint32_t i = lane; i < qn; i += 32) created += table_add(tv, s_queue[i], 1, full);
+    for (uint32_t i = lane; i < qn; i += 32) {
+        const uint64_t key = s_key[i];
+        if (key == kEmpty) { created += table_add(tv, key, 1, full); continue; }
+        created += table_add_buckets(tv, key, 1, full, (tv.home(key) + s_skip[i]) & (tv.cap - 1));
+    }
     __syncwarp();
 }
 
+// Specialised kernel (k <= 32).  Every warp is an independent worker: it pulls
+// tiles of kWarpTile = 256 window starts from an atomic counter, stages them in
+// its private slice of shared memory and only ever executes __syncwarp().  (A
+// first version used 2048-window CTA tiles; ncu showed 30 % of all stall samples
+// at the CTA barrier waiting for the one warp stuck in a long probe.)
 template <int K, int MODE>
 __global__ void __launch_bounds__(kThreads, 3) consume_kernel(const ConsumeParams p) {
     static_assert(K >= 1 && K <= 32, "specialised kernel covers k <= 32");
     constexpr int Q = 8 * ((K + 7 + 7) / 8);  // bytes a thread pulls per strand
-    constexpr int BL = ((kTileW - 8 + Q) + 15) / 16 * 16;
+    constexpr int BL = ((kWarpTile - 8 + Q) + 15) / 16 * 16;
     constexpr int NV = BL / 16;
     constexpr int NX = Q / 8;
     constexpr int NW = (K + 7) / 8;
+    constexpr int NE = BL / 32 + 3;
     constexpr uint64_t MK = (K == 64) ? ~0ULL : ((1ULL << K) - 1);
     constexpr uint64_t MK1 = (1ULL << (K - 1)) - 1;
     constexpr uint64_t TAILMASK = (K % 8) ? (~0ULL >> (8 * (8 - K % 8))) : ~0ULL;
     constexpr bool kCounts = MODE == kModeCount || MODE == kModeRoute;
+    constexpr int kWarps = kThreads / 32;
+    static_assert(NV <= 32 && NE <= 32, "one lane per staged vector / mask word");
 
-    __shared__ __align__(16) uint8_t s_fw[BL];
-    __shared__ __align__(16) uint8_t s_rc[BL];
-    __shared__ __align__(8) uint16_t s_bad[NV + 6];
-    constexpr int NE = BL / 32 + 3;
-    __shared__ __align__(8) uint32_t s_end2[2][NE + (NE & 1)];  // alternates per tile, see below
-    __shared__ __align__(8) uint64_t s_queue[kCounts ? kThreads * kWPT : 1];
-    __shared__ uint64_t s_tile;
+    __shared__ __align__(16) uint8_t s_fw_all[kWarps][BL];
+    __shared__ __align__(16) uint8_t s_rc_all[kWarps][BL];
+    __shared__ __align__(8) uint16_t s_bad_all[kWarps][NV + 6 + ((NV + 6) & 1) + 2];
+    __shared__ __align__(8) uint32_t s_end_all[kWarps][NE + (NE & 1)];
+    __shared__ __align__(8) uint64_t s_queue_all[kCounts ? kWarps : 1][kCounts ? kWPT * 32 + kWPT * 4 : 1];  // keys + resume bytes
 
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *s_fw = s_fw_all[warp], *s_rc = s_rc_all[warp];
+    uint16_t *s_bad = s_bad_all[warp];
+    uint32_t *s_end = s_end_all[warp];
     uint64_t n_counted = 0;
     uint64_t first_bad = ~0ULL;
 
-    for (uint32_t it = 0;; ++it) {
-        // Tiles are handed out dynamically: the grid is sized to what is resident.
-        // Two barriers per tile: slow warps may still be reading the previous tile's
-        // end-mask while fast ones clear the next one, hence the two copies.
-        uint32_t *s_end = s_end2[it & 1];
-        if (tid == 0) s_tile = atomicAdd((unsigned long long *)&p.table.ctrl->tile_counter, 1ULL);
-        for (int i = tid; i < NE; i += kThreads) s_end[i] = 0;
-        __syncthreads();
-        const uint64_t t = s_tile;
+    for (;;) {
+        uint64_t t = 0;
+        if (lane == 0) t = atomicAdd((unsigned long long *)&p.table.ctrl->tile_counter, 1ULL);
+        t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= p.n_tiles) break;
-        const uint64_t w0 = p.tile_base + t * kTileW;
+        const uint64_t w0 = p.tile_base + t * kWarpTile;
 
-        if (tid < NV) stage16<BL>(p, w0, tid, s_fw, s_rc, s_bad);
-        for (uint64_t r = p.tile_first[t] + tid; r < p.n_off; r += kThreads) {
+        if (lane < NE) s_end[lane] = 0;
+        __syncwarp();
+        if (lane < NV) stage16<BL>(p, w0, lane, s_fw, s_rc, s_bad);
+        for (uint64_t r = p.tile_first[t] + lane; r < p.n_off; r += 32) {
             const uint64_t e = p.offsets[r] - 1 - w0;  // last base of read r-1, tile-relative
             if (e >= (uint64_t)BL) break;
             atomicOr(&s_end[e >> 5], 1u << (e & 31));
         }
         bool full = false;
         if (kCounts) full = __ldcg(&p.table.ctrl->size) >= p.table.limit;
-        __syncthreads();
+        __syncwarp();
 
-        const int p0 = tid * kWPT;
+        const int p0 = lane * kWPT;
         const uint32_t *bad32 = reinterpret_cast<const uint32_t *>(s_bad);
         const int wi = p0 >> 5, sh = p0 & 31;
         const uint64_t mb = (((uint64_t)bad32[wi + 1] << 32) | bad32[wi]) >> sh;
@@ -229,83 +251,84 @@ __global__ void __launch_bounds__(kThreads, 3) consume_kernel(const ConsumeParam
                 valid |= 1u << j;
             }
         }
-        if (MODE == kModeFirstBad) continue;
 
-        uint64_t h[kWPT] = {};
-        if (valid) {
-            uint64_t F[NX], R[NX];
-            const uint64_t *f64 = reinterpret_cast<const uint64_t *>(s_fw + p0);
-            const uint64_t *r64 = reinterpret_cast<const uint64_t *>(s_rc + BL - p0 - Q);
+        if (MODE != kModeFirstBad) {
+            uint64_t h[kWPT] = {};
+            if (valid) {
+                uint64_t F[NX], R[NX];
+                const uint64_t *f64 = reinterpret_cast<const uint64_t *>(s_fw + p0);
+                const uint64_t *r64 = reinterpret_cast<const uint64_t *>(s_rc + BL - p0 - Q);
 #pragma unroll
-            for (int i = 0; i < NX; ++i) { F[i] = f64[i]; R[i] = r64[i]; }
+                for (int i = 0; i < NX; ++i) { F[i] = f64[i]; R[i] = r64[i]; }
 
-            auto hash_one = [&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                constexpr int FO = j, RO = Q - K - j;
-                uint64_t a[NW], b[NW];
-                static_for<NW>([&](auto ic) {
-                    constexpr int i = decltype(ic)::value;
-                    a[i] = word_at<FO + 8 * i>(F);
-                    b[i] = word_at<RO + 8 * i>(R);
-                });
-                a[NW - 1] &= TAILMASK;
-                b[NW - 1] &= TAILMASK;
-                bool use_rc = bswap64(b[0]) < bswap64(a[0]);
-                if (NW > 1 && a[0] == b[0]) {  // rare: first 8 bases tie
+                auto hash_one = [&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    constexpr int FO = j, RO = Q - K - j;
+                    uint64_t a[NW], b[NW];
+                    static_for<NW>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        a[i] = word_at<FO + 8 * i>(F);
+                        b[i] = word_at<RO + 8 * i>(R);
+                    });
+                    a[NW - 1] &= TAILMASK;
+                    b[NW - 1] &= TAILMASK;
+                    bool use_rc = bswap64(b[0]) < bswap64(a[0]);
+                    if (NW > 1 && a[0] == b[0]) {  // rare: first 8 bases tie
 #pragma unroll
-                    for (int i = 1; i < NW; ++i) {
-                        if (a[i] != b[i]) { use_rc = bswap64(b[i]) < bswap64(a[i]); break; }
+                        for (int i = 1; i < NW; ++i) {
+                            if (a[i] != b[i]) { use_rc = bswap64(b[i]) < bswap64(a[i]); break; }
+                        }
                     }
-                }
-                uint64_t w[NW];
+                    uint64_t w[NW];
 #pragma unroll
-                for (int i = 0; i < NW; ++i) w[i] = use_rc ? b[i] : a[i];
-                h[j] = ((valid >> j) & 1u) ? murmur_words<K>(w) : 0;
-            };
-            static_for<kWPT>(hash_one);
-        }
-
-        if (MODE == kModeHash) {
-#pragma unroll
-            for (int j = 0; j < kWPT; ++j)
-                if (gp0 + j >= p.w_lo && gp0 + j < p.w_hi) p.hashes_out[gp0 + j - p.w_lo] = h[j];
-        } else if (kCounts) {
-            uint32_t created = 0;
-            if (MODE == kModeRoute) {
-                // hashes owned elsewhere go to the owner's outgoing list (warp-aggregated append)
-                const int lane = tid & 31;
-#pragma unroll
-                for (int j = 0; j < kWPT; ++j) {
-                    const int owner = (int)(h[j] >> p.owner_shift);
-                    const bool remote = h[j] != 0 && owner != p.self_rank;
-                    const unsigned rm = __ballot_sync(0xffffffffu, remote);
-                    if (remote) {
-                        const unsigned peers = __match_any_sync(rm, owner);
-                        const int leader = __ffs(peers) - 1;
-                        uint64_t base = 0;
-                        if (lane == leader)
-                            base = atomicAdd((unsigned long long *)&p.route_counts[owner],
-                                             (unsigned long long)__popc(peers));
-                        base = __shfl_sync(peers, base, leader);
-                        const uint64_t at = base + __popc(peers & ((1u << lane) - 1));
-                        if (at < p.route_cap) p.route_out[owner][at] = h[j];
-                        h[j] = 0;
-                    }
-                }
+                    for (int i = 0; i < NW; ++i) w[i] = use_rc ? b[i] : a[i];
+                    h[j] = ((valid >> j) & 1u) ? murmur_words<K>(w) : 0;
+                };
+                static_for<kWPT>(hash_one);
             }
-            count_hashes8(p.table, h, full, s_queue + (tid >> 5) * (kWPT * 32), n_counted, created);
-            const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
-            if ((tid & 31) == 0 && tot) atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
+
+            if (MODE == kModeHash) {
+#pragma unroll
+                for (int j = 0; j < kWPT; ++j)
+                    if (gp0 + j >= p.w_lo && gp0 + j < p.w_hi) p.hashes_out[gp0 + j - p.w_lo] = h[j];
+            } else if (kCounts) {
+                uint32_t created = 0;
+                if (MODE == kModeRoute) {
+                    // hashes owned elsewhere go to the owner's outgoing list (warp-aggregated append)
+#pragma unroll
+                    for (int j = 0; j < kWPT; ++j) {
+                        const int owner = (int)(h[j] >> p.owner_shift);
+                        const bool remote = h[j] != 0 && owner != p.self_rank;
+                        const unsigned rm = __ballot_sync(0xffffffffu, remote);
+                        if (remote) {
+                            const unsigned peers = __match_any_sync(rm, owner);
+                            const int leader = __ffs(peers) - 1;
+                            uint64_t base = 0;
+                            if (lane == leader)
+                                base = atomicAdd((unsigned long long *)&p.route_counts[owner],
+                                                 (unsigned long long)__popc(peers));
+                            base = __shfl_sync(peers, base, leader);
+                            const uint64_t at = base + __popc(peers & ((1u << lane) - 1));
+                            if (at < p.route_cap) p.route_out[owner][at] = h[j];
+                            h[j] = 0;
+                        }
+                    }
+                }
+                count_hashes8(p.table, h, full, s_queue_all[warp], n_counted, created);
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
+                if (lane == 0 && tot) atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
+            }
         }
+        __syncwarp();  // this warp's shared slice is reused by its next tile
     }
 
     if (MODE == kModeFirstBad) {
         for (int o = 16; o; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
-        if ((tid & 31) == 0 && first_bad != ~0ULL)
+        if (lane == 0 && first_bad != ~0ULL)
             atomicMin((unsigned long long *)&p.table.ctrl->first_bad, (unsigned long long)first_bad);
     } else if (kCounts) {
         for (int o = 16; o; o >>= 1) n_counted += __shfl_xor_sync(0xffffffffu, n_counted, o);
-        if ((tid & 31) == 0 && n_counted)
+        if (lane == 0 && n_counted)
             atomicAdd((unsigned long long *)&p.table.ctrl->counted, (unsigned long long)n_counted);
     }
 }

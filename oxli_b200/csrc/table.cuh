@@ -97,6 +97,36 @@ __device__ __forceinline__ uint32_t table_add(const TableView &t, uint64_t key, 
     return 0;
 }
 
+// Bucket-wise variant used to drain the consume kernels' slow queue: walks 32-byte
+// buckets (two slots per 256-bit load) starting at even slot `i`, which the caller
+// guarantees is not past the key's position (home, or home+2 when the home bucket
+// was seen full of other keys).
+__device__ __forceinline__ uint32_t table_add_buckets(const TableView &t, uint64_t key, uint64_t inc,
+                                                      bool full, uint64_t i) {
+    for (int probe = 0; t.overflow == nullptr || probe < kMaxProbe; probe += 2) {
+        ulonglong2 s[2];
+        load_pair(t.slots + i, s[0], s[1]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (s[q].x == key) {
+                red_add64(&t.slots[i + q].y, inc);
+                return 0;
+            }
+            if (s[q].x == kEmpty) {
+                if (full) { push_overflow(t, key); return 0; }
+                const uint64_t old = atomicCAS((unsigned long long *)&t.slots[i + q].x, kEmpty, key);
+                if (old == kEmpty || old == key) {
+                    red_add64(&t.slots[i + q].y, inc);
+                    return old == kEmpty ? 1u : 0u;
+                }
+            }
+        }
+        i = (i + 2) & (t.cap - 1);
+    }
+    push_overflow(t, key);
+    return 0;
+}
+
 // same, but returns the count after the increment (count_hash, src/lib.rs:100-104);
 // never defers: the caller reserved room.
 __device__ __forceinline__ uint64_t table_add_fetch(const TableView &t, uint64_t key, uint64_t inc,
