@@ -93,12 +93,22 @@ oxg_status oxg_consume_batch_device(oxg_table *t, const uint8_t *d_bases, const 
                                     uint64_t n_reads, uint64_t total_bases, int skip_bad,
                                     uint64_t *total_counted, int64_t *err_read,
                                     uint64_t *err_pos);
+/* hash-only pass over a device-resident batch: d_hashes_out[w] for every window
+ * start w in [0, total_bases - k + 1) of the flat buffer; 0 for windows that hold
+ * a bad byte or straddle two reads.  (First half of the two-kernel pipeline.) */
+oxg_status oxg_hash_batch_device(oxg_table *t, const uint8_t *d_bases, const uint64_t *d_offsets,
+                                 uint64_t n_reads, uint64_t total_bases, uint64_t *d_hashes_out);
+
 /* ---- increment / lookup by hash (src/lib.rs:100-104, 185-194, 675-681) ---- */
 /* counts[h] += 1 for every h; new_counts (nullable) receives the count after
  * each increment (exact for distinct hashes; for duplicates inside one call the
  * values are the counts seen by each increment in some serial order). */
 oxg_status oxg_count_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, uint64_t *new_counts);
-oxg_status oxg_count_hashes_device(oxg_table *t, const uint64_t *d_hashes, uint64_t n);
+/* device-resident list; skip_zero != 0 ignores entries equal to 0 (the hash
+ * stream of oxg_hash_batch_device marks uncountable windows with 0);
+ * *n_counted (nullable) = increments applied */
+oxg_status oxg_count_hashes_device(oxg_table *t, const uint64_t *d_hashes, uint64_t n, int skip_zero,
+                                   uint64_t *n_counted);
 /* counts_out[i] = counts.get(hashes[i]).unwrap_or(0), order-preserving */
 oxg_status oxg_get_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, uint64_t *counts_out);
 /* counts.insert(h, v): overwrite or create (0 is a legal stored value) */

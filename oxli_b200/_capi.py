@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboxli_b200.so")
+LIB_PATH = os.environ.get("OXLI_B200_LIB") or os.path.join(_HERE, "liboxli_b200.so")
 
 OK, ERR_CUDA, ERR_INVALID, ERR_BAD_KMER, ERR_NOMEM, ERR_WRONG_KSIZE, ERR_TOO_SMALL = range(7)
 
@@ -52,8 +52,9 @@ SIGNATURES = {
     "oxg_hash_windows": (C.c_int, [vp, vp, u64, vp]),
     "oxg_consume_batch": (C.c_int, [vp, vp, vp, u64, C.c_int, u64p, C.POINTER(C.c_int64), u64p]),
     "oxg_consume_batch_device": (C.c_int, [vp, vp, vp, u64, u64, C.c_int, u64p, C.POINTER(C.c_int64), u64p]),
+    "oxg_hash_batch_device": (C.c_int, [vp, vp, vp, u64, u64, vp]),
     "oxg_count_hashes": (C.c_int, [vp, vp, u64, vp]),
-    "oxg_count_hashes_device": (C.c_int, [vp, vp, u64]),
+    "oxg_count_hashes_device": (C.c_int, [vp, vp, u64, C.c_int, u64p]),
     "oxg_get_hashes": (C.c_int, [vp, vp, u64, vp]),
     "oxg_set_hash": (C.c_int, [vp, u64, u64]),
     "oxg_erase_hashes": (C.c_int, [vp, vp, u64, u64p]),
@@ -175,14 +176,19 @@ class Table:
             check(st)
         return st, int(total.value), int(er.value), int(ep.value)
 
+    def hash_batch_device(self, d_bases: int, d_offsets: int, n_reads: int, total_bases: int, d_out: int):
+        check(lib.oxg_hash_batch_device(self._h, d_bases, d_offsets, n_reads, total_bases, d_out))
+
     def count_hashes(self, hashes, want_counts: bool = False):
         h = np.ascontiguousarray(hashes, dtype=np.uint64)
         out = np.empty(len(h), dtype=np.uint64) if want_counts else None
         check(lib.oxg_count_hashes(self._h, _ptr(h), len(h), _ptr(out)))
         return out
 
-    def count_hashes_device(self, d_hashes: int, n: int):
-        check(lib.oxg_count_hashes_device(self._h, d_hashes, n))
+    def count_hashes_device(self, d_hashes: int, n: int, skip_zero: bool = False) -> int:
+        c = u64()
+        check(lib.oxg_count_hashes_device(self._h, d_hashes, n, 1 if skip_zero else 0, C.byref(c)))
+        return int(c.value)
 
     def get_hashes(self, hashes) -> np.ndarray:
         h = np.ascontiguousarray(hashes, dtype=np.uint64)

@@ -317,7 +317,7 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
             if (ov) {  // table hit its load limit: grow, then replay the deferred hashes
                 if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
                 TRY(grow_to_fit(t, t->size + ov));
-                count_hashes_kernel<<<grid_for(c, ov, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr);
+                count_hashes_kernel<<<grid_for(c, ov, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr, 0);
                 LAUNCHED();
                 CU(cudaGetLastError());
                 TRY(pull_ctrl(t));
@@ -529,6 +529,17 @@ oxg_status oxg_consume_batch_device(oxg_table *t, const uint8_t *d_bases, const 
     return consume_resident(t, d_bases, d_offsets, nullptr, n_reads, total_bases, skip_bad, total_counted, err_read, err_pos);
 }
 
+oxg_status oxg_hash_batch_device(oxg_table *t, const uint8_t *d_bases, const uint64_t *d_offsets,
+                                 uint64_t n_reads, uint64_t total_bases, uint64_t *d_hashes_out) {
+    ENTER(t);
+    if (!d_bases || !d_offsets || !d_hashes_out) return fail(OXG_ERR_INVALID, "null argument");
+    const uint64_t k = t->k;
+    if (total_bases < k) return OXG_OK;
+    TRY(run_span(t, kModeHash, d_bases, 0, 0, total_bases - k + 1, total_bases, d_offsets, n_reads + 1, d_hashes_out, nullptr));
+    CU(cudaStreamSynchronize(c->stream));
+    return OXG_OK;
+}
+
 // Host batch: stream [w_lo, w_hi) through the two staging buffers.
 static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, const uint64_t *offsets,
                               uint64_t n_reads, uint64_t w_lo, uint64_t w_hi, uint64_t data_end,
@@ -650,14 +661,49 @@ oxg_status oxg_consume_batch(oxg_table *t, const uint8_t *bases, const uint64_t 
 
 // ---- by-hash operations ----------------------------------------------------
 
-oxg_status oxg_count_hashes_device(oxg_table *t, const uint64_t *d_hashes, uint64_t n) {
+// counts a device-resident hash list in launches of <= kLaunchWindows entries; large
+// lists go in optimistically (load-limit deferral + growth + replay) like consume
+static oxg_status count_list_device(oxg_table *t, const uint64_t *d_hashes, uint64_t n, int skip_zero, uint64_t *counted) {
+    DeviceCtx *c = t->ctx;
+    for (uint64_t lo = 0; lo < n; lo += kLaunchWindows) {
+        const uint64_t m = std::min<uint64_t>(kLaunchWindows, n - lo);
+        const bool optimistic = m > kSmallBatch;
+        if (!optimistic) TRY(reserve_keys(t, m));
+        else {
+            if (t->size * 10 > t->cap * 7) TRY(grow_to_fit(t, t->size));
+            TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, m));
+        }
+        TRY(zero_ctrl_fields(t, kFieldCounted, 3));
+        CU(cudaEventRecord(c->ev_t0, c->stream));
+        count_hashes_kernel<<<grid_for(c, (m + 7) / 8, kOpThreads, 8), kOpThreads, 0, c->stream>>>(view_of(t, optimistic), d_hashes + lo, m, nullptr, skip_zero);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(c->ev_t1, c->stream));
+        TRY(pull_ctrl(t));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+        t->last_ms += ms; t->last_launches += 1;
+        if (counted) *counted += t->h_ctrl->counted;
+        const uint64_t ov = t->h_ctrl->overflow;
+        if (ov) {
+            if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
+            TRY(grow_to_fit(t, t->size + ov));
+            count_hashes_kernel<<<grid_for(c, (ov + 7) / 8, kOpThreads, 8), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr, 0);
+            LAUNCHED();
+            CU(cudaGetLastError());
+            TRY(pull_ctrl(t));
+        }
+    }
+    return OXG_OK;
+}
+
+oxg_status oxg_count_hashes_device(oxg_table *t, const uint64_t *d_hashes, uint64_t n, int skip_zero, uint64_t *n_counted) {
     ENTER(t);
+    if (n_counted) *n_counted = 0;
     if (n == 0) return OXG_OK;
-    TRY(reserve_keys(t, n));
-    count_hashes_kernel<<<grid_for(c, n, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), d_hashes, n, nullptr);
-    LAUNCHED();
-    CU(cudaGetLastError());
-    return pull_ctrl(t);
+    if (!d_hashes) return fail(OXG_ERR_INVALID, "null argument");
+    t->last_ms = 0.f; t->last_launches = 0;
+    return count_list_device(t, d_hashes, n, skip_zero, n_counted);
 }
 
 oxg_status oxg_count_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, uint64_t *new_counts) {
@@ -668,7 +714,7 @@ oxg_status oxg_count_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, ui
     TRY(ensure_io(c, 2 * n));
     memcpy(c->h_io, hashes, n * 8);
     CU(cudaMemcpyAsync(c->d_io, c->h_io, n * 8, cudaMemcpyHostToDevice, c->stream));
-    count_hashes_kernel<<<grid_for(c, n, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_io, n, new_counts ? c->d_io + n : nullptr);
+    count_hashes_kernel<<<grid_for(c, n, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_io, n, new_counts ? c->d_io + n : nullptr, 0);
     LAUNCHED();
     CU(cudaGetLastError());
     if (new_counts) CU(cudaMemcpyAsync(c->h_io + n, c->d_io + n, n * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1080,7 +1126,7 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
         const uint64_t ov = t->h_ctrl->overflow;
         if (ov) {
             TRY(grow_to_fit(t, t->size + ov));
-            count_hashes_kernel<<<grid_for(c, ov, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr);
+            count_hashes_kernel<<<grid_for(c, ov, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr, 0);
             LAUNCHED();
             CU(cudaGetLastError());
             TRY(pull_ctrl(t));

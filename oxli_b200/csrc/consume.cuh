@@ -35,6 +35,10 @@ __device__ __forceinline__ void static_for(F &&f) {
     static_for_impl(f, std::make_integer_sequence<int, N>{});
 }
 
+#ifndef OXG_MIN_CTAS
+#define OXG_MIN_CTAS 3  // resident CTAs per SM the specialised kernel is compiled for
+#endif
+
 constexpr int kTileW = 2048;  // window starts per tile
 constexpr int kThreads = 256;
 constexpr int kWPT = kTileW / kThreads;  // 8 consecutive windows per thread
@@ -184,7 +188,7 @@ __device__ __forceinline__ void count_hashes8(const TableView &tv, const uint64_
 // first version used 2048-window CTA tiles; ncu showed 30 % of all stall samples
 // at the CTA barrier waiting for the one warp stuck in a long probe.)
 template <int K, int MODE>
-__global__ void __launch_bounds__(kThreads, 3) consume_kernel(const ConsumeParams p) {
+__global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const ConsumeParams p) {
     static_assert(K >= 1 && K <= 32, "specialised kernel covers k <= 32");
     constexpr int Q = 8 * ((K + 7 + 7) / 8);  // bytes a thread pulls per strand
     constexpr int BL = ((kWarpTile - 8 + Q) + 15) / 16 * 16;

@@ -25,16 +25,56 @@ __global__ void init_slots_kernel(ulonglong2 *slots, uint64_t cap) {
 }
 
 // count_hash for a list (src/lib.rs:100-104); room was reserved by the host.
-__global__ void count_hashes_kernel(TableView t, const uint64_t *__restrict__ hashes, uint64_t n,
-                                    uint64_t *__restrict__ new_counts) {
+// Without new_counts: 8 keys per thread per round, all home buckets (one 256-bit
+// load each) requested before the first is examined; zero keys are skipped when
+// skip_zero is set (the hash stream of the two-kernel pipeline marks bad windows 0).
+__global__ void __launch_bounds__(kOpThreads) count_hashes_kernel(TableView t, const uint64_t *__restrict__ hashes, uint64_t n,
+                                    uint64_t *__restrict__ new_counts, int skip_zero) {
     uint32_t created = 0;
-    for (uint64_t i = gtid(); i < n; i += gstride()) {
-        const uint64_t h = hashes[i];
-        if (new_counts) new_counts[i] = table_add_fetch(t, h, 1, &created);
-        else created += table_add(t, h, 1, false);
+    uint64_t counted = 0;
+    if (new_counts) {
+        for (uint64_t i = gtid(); i < n; i += gstride())
+            new_counts[i] = table_add_fetch(t, hashes[i], 1, &created);
+    } else {
+        constexpr int U = 8;
+        const uint64_t stride = gstride();
+        for (uint64_t base = gtid(); base < n; base += stride * U) {
+            // at the load limit new keys are deferred to the overflow list (if there is one)
+            const bool full = t.overflow != nullptr && __ldcg(&t.ctrl->size) >= t.limit;
+            uint64_t h[U], idx[U];
+            ulonglong2 a[U], b[U];
+            bool live[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint64_t i = base + u * stride;
+                live[u] = i < n;
+                h[u] = live[u] ? __ldcs(hashes + i) : 0;
+                if (skip_zero && h[u] == 0) live[u] = false;
+                if (h[u] == kEmpty) { if (live[u]) { created += table_add(t, h[u], 1, full); ++counted; } live[u] = false; }
+                idx[u] = t.home(h[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (live[u]) load_pair(t.slots + idx[u], a[u], b[u]);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (!live[u]) continue;
+                ++counted;
+                if (a[u].x == h[u]) red_add64(&t.slots[idx[u]].y, 1);
+                else if (b[u].x == h[u]) red_add64(&t.slots[idx[u] + 1].y, 1);
+                else {
+                    const bool redo = a[u].x == kEmpty || b[u].x == kEmpty;
+                    created += table_add_buckets(t, h[u], 1, full, (idx[u] + (redo ? 0 : 2)) & (t.cap - 1));
+                }
+            }
+        }
     }
     const uint64_t tot = warp_sum(created);
-    if ((threadIdx.x & 31) == 0 && tot) atomicAdd((unsigned long long *)&t.ctrl->size, (unsigned long long)tot);
+    counted = warp_sum(counted);
+    if ((threadIdx.x & 31) == 0) {
+        if (tot) atomicAdd((unsigned long long *)&t.ctrl->size, (unsigned long long)tot);
+        if (counted) atomicAdd((unsigned long long *)&t.ctrl->counted, (unsigned long long)counted);
+    }
 }
 
 // get_hash / get_hash_array (src/lib.rs:185-194)
