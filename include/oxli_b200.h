@@ -109,6 +109,9 @@ oxg_status oxg_count_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, ui
  * *n_counted (nullable) = increments applied */
 oxg_status oxg_count_hashes_device(oxg_table *t, const uint64_t *d_hashes, uint64_t n, int skip_zero,
                                    uint64_t *n_counted);
+/* counts[keys[i]] += vals[i], creating keys as needed (a created key may keep the
+ * value 0).  Bulk form of count_hash/__setitem__ used by load() (src/lib.rs:297-322). */
+oxg_status oxg_add_pairs(oxg_table *t, const uint64_t *keys, const uint64_t *vals, uint64_t n);
 /* counts_out[i] = counts.get(hashes[i]).unwrap_or(0), order-preserving */
 oxg_status oxg_get_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, uint64_t *counts_out);
 /* counts.insert(h, v): overwrite or create (0 is a legal stored value) */

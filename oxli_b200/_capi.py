@@ -55,6 +55,7 @@ SIGNATURES = {
     "oxg_hash_batch_device": (C.c_int, [vp, vp, vp, u64, u64, vp]),
     "oxg_count_hashes": (C.c_int, [vp, vp, u64, vp]),
     "oxg_count_hashes_device": (C.c_int, [vp, vp, u64, C.c_int, u64p]),
+    "oxg_add_pairs": (C.c_int, [vp, vp, vp, u64]),
     "oxg_get_hashes": (C.c_int, [vp, vp, u64, vp]),
     "oxg_set_hash": (C.c_int, [vp, u64, u64]),
     "oxg_erase_hashes": (C.c_int, [vp, vp, u64, u64p]),
@@ -189,6 +190,12 @@ class Table:
         c = u64()
         check(lib.oxg_count_hashes_device(self._h, d_hashes, n, 1 if skip_zero else 0, C.byref(c)))
         return int(c.value)
+
+    def add_pairs(self, keys, vals):
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        v = np.ascontiguousarray(vals, dtype=np.uint64)
+        assert len(k) == len(v)
+        check(lib.oxg_add_pairs(self._h, _ptr(k), _ptr(v), len(k)))
 
     def get_hashes(self, hashes) -> np.ndarray:
         h = np.ascontiguousarray(hashes, dtype=np.uint64)

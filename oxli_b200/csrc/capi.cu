@@ -723,6 +723,24 @@ oxg_status oxg_count_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, ui
     return OXG_OK;
 }
 
+oxg_status oxg_add_pairs(oxg_table *t, const uint64_t *keys, const uint64_t *vals, uint64_t n) {
+    ENTER(t);
+    if (n == 0) return OXG_OK;
+    if (!keys || !vals) return fail(OXG_ERR_INVALID, "null argument");
+    TRY(reserve_keys(t, n));
+    TRY(ensure_io(c, 2 * n));
+    memcpy(c->h_io, keys, n * 8);
+    memcpy(c->h_io + n, vals, n * 8);
+    CU(cudaMemcpyAsync(c->d_io, c->h_io, 2 * n * 8, cudaMemcpyHostToDevice, c->stream));
+    add_pairs_kernel<<<grid_for(c, n, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_io, c->d_io + n, n);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    // the out-of-band key's side entry must exist even when its value is 0
+    for (uint64_t i = 0; i < n; ++i)
+        if (keys[i] == kEmpty) { const uint64_t one = 1; CU(cudaMemcpyAsync(&t->d_ctrl->side_present, &one, 8, cudaMemcpyHostToDevice, c->stream)); break; }
+    return pull_ctrl(t);
+}
+
 oxg_status oxg_get_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, uint64_t *counts_out) {
     ENTER(t);
     if (n == 0) return OXG_OK;
@@ -1030,8 +1048,7 @@ oxg_status oxg_cosine(oxg_table *a, oxg_table *b, double *out) {
     cosine_kernel<<<grid_for(c, a->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(a, false), view_of(b, false), c->d_f64);
     LAUNCHED();
     TableView none = view_of(a, false);
-    none.slots = nullptr;
-    TRY(zero_ctrl_fields(b, kFieldScratch, 1));
+    none.slots = nullptr;  // norm-only pass over b: adds nothing to any dot product
     cosine_kernel<<<grid_for(c, b->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(b, false), none, c->d_f64 + 1);
     LAUNCHED();
     CU(cudaGetLastError());

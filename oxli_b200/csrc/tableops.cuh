@@ -77,6 +77,14 @@ __global__ void __launch_bounds__(kOpThreads) count_hashes_kernel(TableView t, c
     }
 }
 
+// counts[key] += val for (key,val) pairs; creates keys (also with val == 0)
+__global__ void add_pairs_kernel(TableView t, const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals, uint64_t n) {
+    uint32_t created = 0;
+    for (uint64_t i = gtid(); i < n; i += gstride()) created += table_add(t, keys[i], vals[i], false);
+    const uint64_t tot = warp_sum(created);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd((unsigned long long *)&t.ctrl->size, (unsigned long long)tot);
+}
+
 // get_hash / get_hash_array (src/lib.rs:185-194)
 __global__ void get_hashes_kernel(TableView t, const uint64_t *__restrict__ hashes, uint64_t n,
                                   uint64_t *__restrict__ out) {

@@ -1,0 +1,283 @@
+"""The drop-in `oxli.KmerCountTable` (C++ mirror over the C ABI) against the
+behaviours the reference's own test-suite pins (src/python/tests/*.py, cited per
+test) and against the CPU oracle."""
+import gzip
+import json
+
+import numpy as np
+import pytest
+
+from oracle import OracleTable
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oxli():
+    import oxli as mod
+
+    return mod
+
+
+def make(oxli, k, kmers, **kw):
+    t = oxli.KmerCountTable(k, **kw)
+    for km in kmers:
+        t.count(km)
+    return t
+
+
+# ---- test_basic.py -----------------------------------------------------------
+
+def test_count_get_and_hash(oxli, goldens):
+    t = oxli.KmerCountTable(4)
+    assert t.get("ATCG") == 0 and t.count("ATCG") == 1 and t.get("ATCG") == 1
+    for e in goldens["kmer_hash"]:
+        assert oxli.KmerCountTable(len(e["kmer"])).hash_kmer(e["kmer"]) == e["hash"]
+    t = oxli.KmerCountTable(ksize=31)
+    kmer = "TAAACCCTAACCCTAACCCTAACCCTAACCC"
+    h = t.hash_kmer(kmer)
+    assert t.get_hash(h) == 0 and t.count_hash(h) == 1 and t.get_hash(h) == 1
+    assert t.count(kmer) == 2 and t.count(kmer) == 3 and t.count_hash(h) == 4 and t.get(kmer) == 4
+    assert t.hash_kmer("aaaccctaaccctaaccctaaccctaaccca".upper()) == t.hash_kmer("aaaccctaaccctaaccctaaccctaaccca")
+
+
+def test_wrong_ksize_and_bad_kmer(oxli):
+    t = oxli.KmerCountTable(3)
+    with pytest.raises(ValueError):
+        t.count("ATCG")
+    with pytest.raises(ValueError):
+        t.get("ATCG")
+    with pytest.raises(RuntimeError, match="wrong ksize"):
+        t.hash_kmer("ATCG")
+    with pytest.raises(RuntimeError):
+        t.hash_kmer("ATN")
+    with pytest.raises(OverflowError):
+        oxli.KmerCountTable(256)
+    with pytest.raises(OverflowError):
+        oxli.KmerCountTable(-1)
+
+
+def test_consume_modes(oxli):
+    t = oxli.KmerCountTable(4)
+    assert t.consume("ATCGG") == 2
+    assert (t.get("ATCG"), t.get("TCGG"), t.get("CCGA")) == (1, 1, 1)
+    t = oxli.KmerCountTable(4)
+    with pytest.raises(ValueError, match="bad k-mer encountered at position 2"):
+        t.consume("ATCGGX", skip_bad_kmers=False)
+    assert t.get("ATCG") == 1 and t.consumed == 0
+    with pytest.raises(ValueError, match="bad k-mer encountered at position 0"):
+        oxli.KmerCountTable(4).consume("XATCGG", skip_bad_kmers=False)
+    t = oxli.KmerCountTable(4)
+    assert t.consume("XATCGG") == 2 and t.get("CCGA") == 1
+
+
+def test_get_hash_array(oxli):
+    t = make(oxli, 3, ["AAA", "TTT", "AAC"])
+    keys = [t.hash_kmer("AAA"), t.hash_kmer("AAC"), t.hash_kmer("GGG")]
+    assert t.get_hash_array(keys) == [2, 1, 0]
+    assert t.get_hash_array(keys[::-1]) == [0, 1, 2]
+    assert t.get_hash(12774992397053849803) == 0
+
+
+# ---- test_attr.py / test_dunders.py --------------------------------------------
+
+def test_attributes(oxli):
+    t = make(oxli, 3, ["AAA", "TTT", "AAC"])
+    assert set(t.hashes) == {10679328328772601858, 6579496673972597301}
+    assert t.version == "0.3.0"  # Cargo.toml [package] version of the reference
+    assert t.consumed == 9 and t.sum_counts == 3
+    t.consume("AAAAXTT")
+    assert t.consumed == 16
+    assert oxli.KmerCountTable(31).consumed == 0
+    assert oxli.KmerCountTable(4).consume("ACG") == 0
+
+
+def test_dunders(oxli):
+    t = make(oxli, 4, ["AAAA", "TTTT", "AATT", "GGGG", "GGGG"])
+    assert len(t) == 3
+    assert sorted(t) == sorted([(17832910516274425539, 2), (382727017318141683, 1), (73459868045630124, 2)])
+    assert t["GGGG"] == 2
+    t["GGGG"] = 7
+    t["ACGT"] = 0
+    assert t["CCCC"] == 7 and t["ACGT"] == 0 and len(t) == 4
+    assert list(t) == t.dump() == t.dump(file=None, sortcounts=False, sortkeys=False)
+
+
+# ---- test_histo.py ---------------------------------------------------------------
+
+def test_histo_min_max(oxli):
+    t = oxli.KmerCountTable(4)
+    assert (t.min, t.max, t.histo(zero=False), t.histo(zero=True)) == (0, 0, [], [(0, 0)])
+    t.count("AAAA"); t.count("TTTT"); t.consume("CCCCCC")
+    assert t.min == 2 and t.max == 3
+    t = make(oxli, 4, ["AAAA", "AAAA", "TTTT", "CCCC"])
+    assert t.histo(zero=False) == [(1, 1), (3, 1)]
+    assert t.histo() == [(0, 0), (1, 1), (2, 0), (3, 1)]
+
+
+# ---- test_setops.py / test_metrics.py ----------------------------------------------
+
+def test_set_ops_and_jaccard(oxli):
+    a = make(oxli, 4, ["AAAA", "AATT", "GGGG"])
+    b = make(oxli, 4, ["AATT", "GGGG", "CCAA"])
+    ha = {k: a.hash_kmer(k) for k in ("AAAA", "AATT", "GGGG", "CCAA")}
+    assert a.union(b) == (a | b) == set(ha.values())
+    assert a.intersection(b) == (a & b) == {ha["AATT"], ha["GGGG"]}
+    assert a.difference(b) == (a - b) == {ha["AAAA"]}
+    assert a.symmetric_difference(b) == (a ^ b) == {ha["AAAA"], ha["CCAA"]}
+    assert a.jaccard(b) == 2 / 4 and a.jaccard(a) == 1.0
+    e1, e2 = oxli.KmerCountTable(4), oxli.KmerCountTable(4)
+    assert e1.jaccard(e2) == 1.0 and e1.jaccard(a) == 0.0
+    assert isinstance(a.union(b), set)
+
+
+def test_cosine(oxli):
+    a, b = oxli.KmerCountTable(4), oxli.KmerCountTable(4)
+    a["AAAA"], a["AATT"], a["GGGG"] = 5, 4, 0
+    b["AAAA"], b["AATT"], b["GGGG"], b["CCAA"] = 1, 2, 3, 4
+    want = (5 * 1 + 4 * 2) / (np.sqrt(25 + 16) * np.sqrt(1 + 4 + 9 + 16))
+    assert a.cosine(b) == pytest.approx(want, rel=1e-9)
+    assert a.cosine(a) == pytest.approx(1.0, rel=1e-12)
+    assert oxli.KmerCountTable(4).cosine(a) == 0.0
+
+
+# ---- test_add.py / test_remove.py ---------------------------------------------------
+
+def test_add(oxli, capfd):
+    a, b = oxli.KmerCountTable(5), oxli.KmerCountTable(5)
+    a.consume("ATGCATGC"); b.consume("CATGGCATG")
+    oa, ob = OracleTable(5), OracleTable(5)
+    oa.consume("ATGCATGC"); ob.consume("CATGGCATG")
+    assert a.add(b) == oa.add(ob)
+    assert sorted(a) == [(int(k), int(v)) for k, v in zip(*oa.items_sorted())]
+    assert a.consumed == 17
+    out = capfd.readouterr().out
+    assert "k-mer counts to the table" in out and "new keys to the table" in out
+    with pytest.raises(ValueError):
+        a.add(oxli.KmerCountTable(4))
+    big = oxli.KmerCountTable(5)
+    assert big.consume("ATGC" * 100000) == 399996
+    assert a.add(big)[0] == 399996
+
+
+def test_remove(oxli):
+    t = make(oxli, 4, ["AAAA", "TTTT", "AATT", "GGGG", "GGGG", "ACGT", "ACGT", "ACGT"])
+    t.drop("GGGG")
+    assert t.get("GGGG") == 0 and len(t) == 3
+    t.drop_hash(t.hash_kmer("AATT")); t.drop_hash(12345)
+    assert len(t) == 2
+    t = make(oxli, 4, ["AAAA", "TTTT", "AATT", "GGGG", "GGGG", "ACGT", "ACGT", "ACGT"])
+    assert t.mincut(2) == 1 and len(t) == 3
+    assert t.maxcut(2) == 1 and t.get("ACGT") == 0 and len(t) == 2
+
+
+# ---- test_dump.py / test_canonicalization.py / test_kmers_and_hashes.py ---------------
+
+def test_dump(oxli, tmp_path):
+    t = make(oxli, 4, ["AAAA", "TTTT", "AATT", "GGGG", "GGGG"], store_kmers=True)
+    with pytest.raises(ValueError, match="Cannot sort by both counts and keys at the same time."):
+        t.dump(file=None, sortcounts=True, sortkeys=True)
+    assert t.dump(sortcounts=True) == [(382727017318141683, 1), (73459868045630124, 2), (17832910516274425539, 2)]
+    assert t.dump(sortkeys=True) == [(73459868045630124, 2), (382727017318141683, 1), (17832910516274425539, 2)]
+    path = tmp_path / "dump.tsv"
+    assert t.dump(file=str(path), sortkeys=True) == []
+    assert path.read_text() == "73459868045630124\t2\n382727017318141683\t1\n17832910516274425539\t2\n"
+    with pytest.raises(OSError):
+        t.dump(file="", sortkeys=True)
+    assert t.dump_kmers(sortkeys=True) == [("AAAA", 2), ("AATT", 1), ("CCCC", 2)]
+    assert t.dump_kmers(sortcounts=True) == [("AATT", 1), ("AAAA", 2), ("CCCC", 2)]
+    with pytest.raises(ValueError, match="Cannot sort by both counts and kmers at the same time."):
+        t.dump_kmers(sortcounts=True, sortkeys=True)
+    with pytest.raises(ValueError):
+        oxli.KmerCountTable(4).dump_kmers()
+    assert oxli.KmerCountTable(4, store_kmers=True).dump() == []
+
+
+def test_canon(oxli):
+    t = oxli.KmerCountTable(4)
+    assert t.canon("TTTT") == "AAAA" and t.canon("acgt") == "ACGT" and t.canon("GGTT") == "AACC"
+    with pytest.raises(ValueError, match="kmer size does not match count table ksize"):
+        t.canon("AAA")
+    with pytest.raises(ValueError, match="kmer contains invalid characters"):
+        t.canon("AANT")
+
+
+def test_kmers_and_hashes(oxli, capfd):
+    t = oxli.KmerCountTable(4)
+    assert t.kmers_and_hashes("ATAAACC") == [("ATAA", 179996601836427478), ("TAAA", 15286642655859448092),
+                                              ("AAAC", 9097280691811734508), ("AACC", 6779379503393060785)]
+    assert t.kmers_and_hashes("acgttg") == [("ACGT", 2597925387403686983), ("AACG", 7952982457453691616),
+                                             ("CAAC", 7315150081962684964)]
+    x = t.kmers_and_hashes("aattxttgg", False)
+    assert x == [("AATT", 382727017318141683), ("", 0), ("", 0), ("", 0), ("", 0), ("CCAA", 1798905482136869687)]
+    assert "bad k-mer at position 2: ATTX" in capfd.readouterr().err
+    assert t.kmers_and_hashes("aattxttgg", True) == [("AATT", 382727017318141683), ("CCAA", 1798905482136869687)]
+
+
+def test_store_kmers(oxli, capfd):
+    t = oxli.KmerCountTable(ksize=3, store_kmers=True)
+    assert t.consume("XAAAAAXGGGG") == 5 and len(t) == 2
+    err = capfd.readouterr().err
+    for msg in ("bad k-mer at position 1: XAA", "bad k-mer at position 5: AAX", "bad k-mer at position 7: XGG"):
+        assert msg in err
+    assert t.unhash(t.hash_kmer("AAA")) == "AAA" and t.unhash(t.hash_kmer("GGG")) == "CCC"
+    with pytest.raises(KeyError, match="Warning: Hash 1234567890 not found in table."):
+        t.unhash(1234567890)
+    with pytest.raises(ValueError, match="K-mer storage is not enabled."):
+        oxli.KmerCountTable(3).unhash(5)
+    t = oxli.KmerCountTable(4, store_kmers=True)
+    assert t.count("AAAA") == 1 and t.count("TTTT") == 2 and t.unhash(t.hash_kmer("TTTT")) == "AAAA"
+    assert t.consume("AAAAACCCC") == 6 and t.get("AAAA") == 4
+
+
+# ---- test_serialization.py ---------------------------------------------------------------
+
+def test_serialization(oxli, tmp_path, capfd):
+    t = make(oxli, 4, ["AAAA", "TTTT", "AATT"])
+    d = json.loads(t.serialize_json())
+    assert d["ksize"] == 4 and d["version"] == t.version and d["consumed"] == 12
+    assert d["counts"] == {"17832910516274425539": 2, "382727017318141683": 1} and d["hash_to_kmer"] is None
+    path = str(tmp_path / "save.json")
+    t.save(path)
+    assert json.loads(gzip.open(path, "rt").read()) == d  # gzip(JSON), src/lib.rs:275-293
+    back = oxli.KmerCountTable.load(path)
+    assert sorted(back) == sorted(t) and back.consumed == 12 and back.get("TTTT") == 2
+    with gzip.open(path, "wt") as f:
+        json.dump(json.loads(t.serialize_json().replace("0.3.0", "0.0.1")), f)
+    oxli.KmerCountTable.load(path)
+    assert "loaded version is 0.0.1, but current version is 0.3.0" in capfd.readouterr().err
+    bad = tmp_path / "bad.json"
+    bad.write_text("hello, world")
+    with pytest.raises(RuntimeError, match="Deserialization error:"):
+        oxli.KmerCountTable.load(str(bad))
+    with pytest.raises(OSError, match="No such file or directory"):
+        oxli.KmerCountTable.load(str(tmp_path / "nope" / "x.json"))
+    with pytest.raises(OSError):
+        t.save(str(tmp_path / "nope" / "x.json"))
+    s = make(oxli, 4, ["AAAA"], store_kmers=True)
+    s.save(path)
+    assert oxli.KmerCountTable.load(path).unhash(s.hash_kmer("AAAA")) == "AAAA"
+
+
+# ---- batch supersets + oracle cross-check ---------------------------------------------------
+
+def test_consume_many_and_buffer_match_oracle(oxli, example_seq):
+    reads = [example_seq[i:i + 150] for i in range(0, 60000, 97)]
+    reads[5] = reads[5][:70] + "N" + reads[5][71:]
+    reads.append("")
+    reads.append("ACGT")
+    a, b, c = (oxli.KmerCountTable(21) for _ in range(3))
+    ora = OracleTable(21)
+    want = sum(ora.consume(r) for r in reads)
+    assert sum(a.consume(r) for r in reads) == want
+    assert b.consume_many(reads) == want
+    flat = np.frombuffer("".join(reads).encode(), dtype=np.uint8)
+    offs = np.zeros(len(reads) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(r) for r in reads])
+    assert c.consume_buffer(flat, offs) == want
+    items = [(int(k), int(v)) for k, v in zip(*ora.items_sorted())]
+    assert sorted(a) == sorted(b) == sorted(c) == items
+    assert a.consumed == b.consumed == c.consumed == ora.consumed
+    assert a.histo(zero=False) == ora.histo(zero=False) and a.jaccard(b) == 1.0
+    with pytest.raises(ValueError, match=r"bad k-mer encountered at position 50 \(read 5\)"):
+        oxli.KmerCountTable(21).consume_many(reads, skip_bad_kmers=False)

@@ -331,8 +331,8 @@ def test_export_order_is_stable(capi):
 def test_set_operations_and_similarity(capi):
     rng = np.random.default_rng(4)
     pool = rng.integers(0, 2**64 - 1, size=30000, dtype=np.uint64)
-    ka = np.concatenate([pool[:20000], [2**64 - 1]]).astype(np.uint64)
-    kb = np.concatenate([pool[10000:], [2**64 - 1, 0]]).astype(np.uint64)
+    ka = np.concatenate([pool[:20000], np.array([2**64 - 1], dtype=np.uint64)])
+    kb = np.concatenate([pool[10000:], np.array([2**64 - 1, 0], dtype=np.uint64)])
     a, b, oa, ob = capi.Table(21), capi.Table(21), OracleTable(21), OracleTable(21)
     sa, sb = rng.choice(ka, 50000), rng.choice(kb, 50000)
     a.count_hashes(sa); b.count_hashes(sb)
