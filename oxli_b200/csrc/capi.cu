@@ -1127,6 +1127,7 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
         p.tile_first = c->d_tile_first; p.table = view_of(t, true); p.ksize = t->k;
         p.owner_shift = lg == 0 ? 63 : 64 - lg;  // with one rank every hash >> 63 is 0 or 1; handled below
         p.self_rank = self_rank;
+        p.n_ranks = n_ranks;
         for (int r = 0; r < n_ranks; ++r) p.route_out[r] = d_out ? d_out[r] : nullptr;
         p.route_counts = d_out_counts; p.route_cap = out_cap;
         if (lg == 0) return fail(OXG_ERR_INVALID, "use oxg_consume_batch_device when n_ranks == 1");

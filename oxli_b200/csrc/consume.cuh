@@ -69,6 +69,7 @@ struct ConsumeParams {
     // kModeRoute
     int owner_shift;       // owner(h) = h >> owner_shift
     int self_rank;
+    int n_ranks;
     uint64_t *route_out[kMaxRanks];
     uint64_t *route_counts;
     uint64_t route_cap;
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
     __shared__ __align__(8) uint16_t s_bad_all[kWarps][NV + 6 + ((NV + 6) & 1) + 2];
     __shared__ __align__(8) uint32_t s_end_all[kWarps][NE + (NE & 1)];
     __shared__ __align__(8) uint64_t s_queue_all[kCounts ? kWarps : 1][kCounts ? kWPT * 32 + kWPT * 4 : 1];  // keys + resume bytes
+    __shared__ __align__(8) uint64_t s_route_all[MODE == kModeRoute ? kWarps : 1][MODE == kModeRoute ? kMaxRanks / 2 + kMaxRanks : 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *s_fw = s_fw_all[warp], *s_rc = s_rc_all[warp];
@@ -298,25 +300,33 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
             } else if (kCounts) {
                 uint32_t created = 0;
                 if (MODE == kModeRoute) {
-                    // hashes owned elsewhere go to the owner's outgoing list (warp-aggregated append)
+                    // Hashes owned by another rank go to that rank's outgoing list.  Positions
+                    // are handed out per warp tile: shared-memory counters rank the tile's
+                    // hashes per owner, then ONE global atomic per owner reserves the run.
+                    uint32_t *s_rcnt = reinterpret_cast<uint32_t *>(s_route_all[warp]);
+                    uint64_t *s_rbase = s_route_all[warp] + kMaxRanks / 2;
+                    if (lane < kMaxRanks) s_rcnt[lane] = 0;
+                    __syncwarp();
+                    uint32_t slot_in_run[kWPT];
 #pragma unroll
                     for (int j = 0; j < kWPT; ++j) {
                         const int owner = (int)(h[j] >> p.owner_shift);
-                        const bool remote = h[j] != 0 && owner != p.self_rank;
-                        const unsigned rm = __ballot_sync(0xffffffffu, remote);
-                        if (remote) {
-                            const unsigned peers = __match_any_sync(rm, owner);
-                            const int leader = __ffs(peers) - 1;
-                            uint64_t base = 0;
-                            if (lane == leader)
-                                base = atomicAdd((unsigned long long *)&p.route_counts[owner],
-                                                 (unsigned long long)__popc(peers));
-                            base = __shfl_sync(peers, base, leader);
-                            const uint64_t at = base + __popc(peers & ((1u << lane) - 1));
+                        if (h[j] != 0 && owner != p.self_rank) slot_in_run[j] = atomicAdd(&s_rcnt[owner], 1u);
+                    }
+                    __syncwarp();
+                    if (lane < p.n_ranks && s_rcnt[lane])
+                        s_rbase[lane] = atomicAdd((unsigned long long *)&p.route_counts[lane], (unsigned long long)s_rcnt[lane]);
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < kWPT; ++j) {
+                        const int owner = (int)(h[j] >> p.owner_shift);
+                        if (h[j] != 0 && owner != p.self_rank) {
+                            const uint64_t at = s_rbase[owner] + slot_in_run[j];
                             if (at < p.route_cap) p.route_out[owner][at] = h[j];
                             h[j] = 0;
                         }
                     }
+                    __syncwarp();
                 }
                 count_hashes8(p.table, h, full, s_queue_all[warp], n_counted, created);
                 const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
