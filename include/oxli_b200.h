@@ -161,19 +161,35 @@ oxg_status oxg_cosine(oxg_table *a, oxg_table *b, double *out);
 oxg_status oxg_merge(oxg_table *dst, oxg_table *src, uint64_t *counts_added, uint64_t *new_keys);
 
 /* ---- multi-GPU building blocks (table sharded by the high bits of the hash;
- * one process per GPU, the exchange itself is done by the caller: NCCL
- * all-to-all or peer stores) ------------------------------------------------
- * Hash a device-resident batch; hashes owned by `self_rank` (owner(h) =
- * h >> (64 - log2 n_ranks)) are counted into `t` directly, the others are
- * appended to d_out[owner] (capacity out_cap entries each).  d_out_counts
- * (n_ranks entries, device) receives the number appended per destination;
- * counts are also copied to out_counts (host).  n_ranks must be a power of two
- * <= 64. */
+ * one process per GPU) -------------------------------------------------------
+ * Hash the reads covering bytes [base_lo, base_hi) of a device-resident batch
+ * (both must be read boundaries; d_offsets is the whole batch's CSR array).
+ * Hashes owned by `self_rank` (owner(h) = h >> (64 - log2 n_ranks)) are counted
+ * into `t` directly; the others are appended to d_out[owner] (capacity out_cap
+ * entries each) -- d_out[] may point into PEER memory (oxg_ipc_import), in which
+ * case the kernel's stores are the exchange.  d_out_counts (n_ranks entries,
+ * device) receives the number appended per destination and is copied to
+ * out_counts (host).  The same launch also absorbs hashes that other ranks
+ * routed here earlier: n_absorb device segments d_absorb[i] of absorb_n[i]
+ * hashes (host arrays; n_absorb may be 0).  *local_counted = k-mers of this
+ * rank's reads counted locally, *absorbed = received hashes counted.
+ * n_ranks: power of two, 2..16; k = 21 or 31. */
 oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const uint64_t *d_offsets,
-                                  uint64_t n_reads, uint64_t total_bases, int n_ranks,
+                                  uint64_t n_reads, uint64_t base_lo, uint64_t base_hi, int n_ranks,
                                   int self_rank, uint64_t *const *d_out, uint64_t out_cap,
                                   uint64_t *d_out_counts, uint64_t *out_counts,
-                                  uint64_t *local_counted);
+                                  uint64_t *local_counted, int n_absorb,
+                                  const uint64_t *const *d_absorb, const uint64_t *absorb_n,
+                                  uint64_t *absorbed);
+
+/* Peer memory for the fused exchange: a rank exports the receive buffer it
+ * allocated with oxg_device_alloc, its peers (other processes, one per GPU of the
+ * same node) import it and pass pointers into it as d_out[] of
+ * oxg_route_batch_device, so the route kernel stores remote hashes straight into
+ * the owner's HBM over NVLink.  handle = 64 bytes (cudaIpcMemHandle_t). */
+oxg_status oxg_ipc_export(int device, void *d_ptr, uint8_t handle_out[64]);
+oxg_status oxg_ipc_import(int device, const uint8_t handle[64], void **d_ptr_out);
+oxg_status oxg_ipc_close(int device, void *d_ptr);
 
 /* ---- synthetic reads for benchmarks ----------------
  * Fills d_bases with n_reads reads of read_len bases drawn from a random genome

@@ -69,7 +69,11 @@ SIGNATURES = {
     "oxg_jaccard": (C.c_int, [vp, vp, C.POINTER(C.c_double)]),
     "oxg_cosine": (C.c_int, [vp, vp, C.POINTER(C.c_double)]),
     "oxg_merge": (C.c_int, [vp, vp, u64p, u64p]),
-    "oxg_route_batch_device": (C.c_int, [vp, vp, vp, u64, u64, C.c_int, C.c_int, C.POINTER(vp), u64, vp, vp, u64p]),
+    "oxg_route_batch_device": (C.c_int, [vp, vp, vp, u64, u64, u64, C.c_int, C.c_int, C.POINTER(vp), u64, vp, vp, u64p,
+                                         C.c_int, C.POINTER(vp), vp, u64p]),
+    "oxg_ipc_export": (C.c_int, [C.c_int, vp, vp]),
+    "oxg_ipc_import": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
+    "oxg_ipc_close": (C.c_int, [C.c_int, vp]),
     "oxg_synth_reads_device": (C.c_int, [C.c_int, vp, u64, C.c_uint32, u64, u64, u64, C.c_uint32, C.c_uint32]),
     "oxg_pinned_alloc": (C.c_int, [u64, C.POINTER(vp)]),
     "oxg_pinned_free": (C.c_int, [vp]),
@@ -317,6 +321,23 @@ def h2d(d_dst: int, src: np.ndarray, device: int = 0) -> None:
 
 def d2h(dst: np.ndarray, d_src: int, device: int = 0) -> None:
     check(lib.oxg_memcpy_d2h(device, dst.ctypes.data, d_src, dst.nbytes))
+
+
+def ipc_export(d_ptr: int, device: int = 0) -> bytes:
+    buf = (C.c_uint8 * 64)()
+    check(lib.oxg_ipc_export(device, d_ptr, buf))
+    return bytes(buf)
+
+
+def ipc_import(handle: bytes, device: int = 0) -> int:
+    buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+    p = vp()
+    check(lib.oxg_ipc_import(device, buf, C.byref(p)))
+    return int(p.value)
+
+
+def ipc_close(d_ptr: int, device: int = 0) -> None:
+    check(lib.oxg_ipc_close(device, d_ptr))
 
 
 def synth_reads_device(d_bases: int, n_reads: int, read_len: int, genome_len: int, seed: int,

@@ -245,7 +245,8 @@ oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
         int per_sm = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         const uint64_t tiles_per_cta = specialised_k(t->k) ? kThreads / 32 : 1;
-        return (int)std::max<uint64_t>(1, std::min<uint64_t>((p.n_tiles + tiles_per_cta - 1) / tiles_per_cta, (uint64_t)c->sms * per_sm));
+        const uint64_t work = p.n_tiles + (MODE == kModeRoute ? p.absorb_first[p.n_absorb] : 0);
+        return (int)std::max<uint64_t>(1, std::min<uint64_t>((work + tiles_per_cta - 1) / tiles_per_cta, (uint64_t)c->sms * per_sm));
     };
     switch (k) {
 #define OXG_CASE(KK)                                                                              \
@@ -290,7 +291,7 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
             if (span <= kSmallBatch) TRY(reserve_keys(t, span));
             else if (t->size * 10 > t->cap * 7) TRY(grow_to_fit(t, t->size));  // > 70 % load: double
             TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, span));
-            TRY(zero_ctrl_fields(t, kFieldCounted, 3));  // counted, overflow, tile_counter
+            TRY(zero_ctrl_fields(t, kFieldCounted, 5));  // counted, overflow, tile_counter, absorb_*
         } else {
             TRY(zero_ctrl_fields(t, kFieldTile, 1));
         }
@@ -673,7 +674,7 @@ static oxg_status count_list_device(oxg_table *t, const uint64_t *d_hashes, uint
             if (t->size * 10 > t->cap * 7) TRY(grow_to_fit(t, t->size));
             TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, m));
         }
-        TRY(zero_ctrl_fields(t, kFieldCounted, 3));
+        TRY(zero_ctrl_fields(t, kFieldCounted, 5));
         CU(cudaEventRecord(c->ev_t0, c->stream));
         count_hashes_kernel<<<grid_for(c, (m + 7) / 8, kOpThreads, 8), kOpThreads, 0, c->stream>>>(view_of(t, optimistic), d_hashes + lo, m, nullptr, skip_zero);
         LAUNCHED();
@@ -1097,42 +1098,64 @@ oxg_status oxg_merge(oxg_table *dst, oxg_table *src, uint64_t *counts_added, uin
 // ---- multi-GPU routing ------------------------------------------------------------
 
 oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const uint64_t *d_offsets,
-                                  uint64_t n_reads, uint64_t total_bases, int n_ranks, int self_rank,
-                                  uint64_t *const *d_out, uint64_t out_cap, uint64_t *d_out_counts,
-                                  uint64_t *out_counts, uint64_t *local_counted) {
+                                  uint64_t n_reads, uint64_t base_lo, uint64_t base_hi, int n_ranks,
+                                  int self_rank, uint64_t *const *d_out, uint64_t out_cap,
+                                  uint64_t *d_out_counts, uint64_t *out_counts, uint64_t *local_counted,
+                                  int n_absorb, const uint64_t *const *d_absorb, const uint64_t *absorb_n,
+                                  uint64_t *absorbed) {
     ENTER(t);
-    if (n_ranks < 1 || n_ranks > kMaxRanks || (n_ranks & (n_ranks - 1)))
-        return fail(OXG_ERR_INVALID, "n_ranks must be a power of two <= %d", kMaxRanks);
+    if (n_ranks < 2 || n_ranks > kMaxRanks || (n_ranks & (n_ranks - 1)))
+        return fail(OXG_ERR_INVALID, "n_ranks must be a power of two in 2..%d (one rank: oxg_consume_batch_device)", kMaxRanks);
     if (self_rank < 0 || self_rank >= n_ranks) return fail(OXG_ERR_INVALID, "self_rank out of range");
+    if (n_absorb < 0 || n_absorb > kMaxRanks) return fail(OXG_ERR_INVALID, "at most %d absorb segments", kMaxRanks);
+    if (base_hi < base_lo) return fail(OXG_ERR_INVALID, "base_hi < base_lo");
+    if (!specialised_k(t->k)) return fail(OXG_ERR_INVALID, "sharded routing is built for k = 21 and 31 only");
     if (local_counted) *local_counted = 0;
+    if (absorbed) *absorbed = 0;
     const uint64_t k = t->k;
     CU(cudaMemsetAsync(d_out_counts, 0, (size_t)n_ranks * 8, c->stream));
     t->last_ms = 0.f; t->last_launches = 0;
-    uint64_t counted = 0;
-    const uint64_t n_win = total_bases >= k ? total_bases - k + 1 : 0;
+    uint64_t counted = 0, absorbed_total = 0;
+    const uint64_t w_end = base_hi - base_lo >= k ? base_hi - k + 1 : base_lo;  // one past the last window start
     int lg = 0;
     while ((1 << lg) < n_ranks) ++lg;
-    uint64_t lo = 0;
-    while (lo < n_win) {
-        const uint64_t hi = std::min(n_win, lo + kLaunchWindows);
+    uint64_t absorb_total = 0;
+    for (int i = 0; i < n_absorb; ++i) absorb_total += absorb_n[i];
+    uint64_t lo = base_lo;
+    bool first = true;
+    while (lo < w_end || (first && absorb_total)) {
+        const uint64_t tile_base = lo & ~(uint64_t)15;
+        const uint64_t hi = std::min<uint64_t>(w_end, tile_base + kLaunchWindows);
         const uint32_t tw = tile_width(t->k);
-        const uint64_t n_tiles = (hi - lo + tw - 1) / tw;
-        TRY(ensure_dev(&c->d_tile_first, &c->tile_first_cap, n_tiles));
+        const uint64_t n_tiles = hi > tile_base ? (hi - tile_base + tw - 1) / tw : 0;
+        TRY(ensure_dev(&c->d_tile_first, &c->tile_first_cap, std::max<uint64_t>(n_tiles, 1)));
         if (t->size * 10 > t->cap * 7) TRY(grow_to_fit(t, t->size));
-        TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, hi - lo));
-        TRY(zero_ctrl_fields(t, kFieldCounted, 3));
+        TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, (hi > lo ? hi - lo : 0) + (first ? absorb_total : 0) + 1));
+        TRY(zero_ctrl_fields(t, kFieldCounted, 5));  // counted, overflow, tile_counter, absorb_counter, absorbed
         ConsumeParams p{};
-        p.bases = d_bases; p.g0 = 0; p.w_lo = lo; p.w_hi = hi; p.data_end = total_bases;
-        p.tile_base = lo; p.n_tiles = n_tiles; p.offsets = d_offsets; p.n_off = n_reads + 1;
+        p.bases = d_bases; p.g0 = 0; p.w_lo = lo; p.w_hi = hi; p.data_end = base_hi;
+        p.tile_base = tile_base; p.n_tiles = n_tiles; p.offsets = d_offsets; p.n_off = n_reads + 1;
         p.tile_first = c->d_tile_first; p.table = view_of(t, true); p.ksize = t->k;
-        p.owner_shift = lg == 0 ? 63 : 64 - lg;  // with one rank every hash >> 63 is 0 or 1; handled below
+        p.owner_shift = 64 - lg;
         p.self_rank = self_rank;
         p.n_ranks = n_ranks;
         for (int r = 0; r < n_ranks; ++r) p.route_out[r] = d_out ? d_out[r] : nullptr;
         p.route_counts = d_out_counts; p.route_cap = out_cap;
-        if (lg == 0) return fail(OXG_ERR_INVALID, "use oxg_consume_batch_device when n_ranks == 1");
-        tile_first_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(d_offsets, n_reads + 1, lo, n_tiles, tw, c->d_tile_first);
-        LAUNCHED();
+        p.n_absorb = 0;
+        p.absorb_first[0] = 0;
+        if (first) {
+            for (int i = 0; i < n_absorb; ++i) {
+                if (!absorb_n[i]) continue;
+                p.absorb_ptr[p.n_absorb] = d_absorb[i];
+                p.absorb_n[p.n_absorb] = absorb_n[i];
+                p.absorb_first[p.n_absorb + 1] = p.absorb_first[p.n_absorb] + (absorb_n[i] + kWarpTile - 1) / kWarpTile;
+                ++p.n_absorb;
+            }
+        }
+        if (n_tiles) {
+            tile_first_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(d_offsets, n_reads + 1, tile_base, n_tiles, tw, c->d_tile_first);
+            LAUNCHED();
+        }
         CU(cudaEventRecord(c->ev_t0, c->stream));
         TRY(launch_consume<kModeRoute>(t, p));
         CU(cudaEventRecord(c->ev_t1, c->stream));
@@ -1141,15 +1164,18 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
         CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
         t->last_ms += ms; t->last_launches += 1;
         counted += t->h_ctrl->counted;
+        absorbed_total += t->h_ctrl->absorbed;
         const uint64_t ov = t->h_ctrl->overflow;
         if (ov) {
+            if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
             TRY(grow_to_fit(t, t->size + ov));
-            count_hashes_kernel<<<grid_for(c, ov, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr, 0);
+            count_hashes_kernel<<<grid_for(c, (ov + 7) / 8, kOpThreads, 8), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr, 0);
             LAUNCHED();
             CU(cudaGetLastError());
             TRY(pull_ctrl(t));
         }
-        lo = hi;
+        lo = std::max(hi, lo);
+        first = false;
     }
     if (out_counts) {
         CU(cudaMemcpyAsync(out_counts, d_out_counts, (size_t)n_ranks * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1158,6 +1184,36 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
             if (out_counts[r] > out_cap) return fail(OXG_ERR_TOO_SMALL, "outgoing list for rank %d overran (%llu > %llu)", r, (unsigned long long)out_counts[r], (unsigned long long)out_cap);
     }
     if (local_counted) *local_counted = counted;
+    if (absorbed) *absorbed = absorbed_total;
+    return OXG_OK;
+}
+
+oxg_status oxg_ipc_export(int device, void *d_ptr, uint8_t handle_out[64]) {
+    DeviceCtx *c;
+    TRY(get_ctx(device, &c));
+    CU(cudaSetDevice(c->dev));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle_out, &h, 64);
+    return OXG_OK;
+}
+
+oxg_status oxg_ipc_import(int device, const uint8_t handle[64], void **d_ptr_out) {
+    DeviceCtx *c;
+    TRY(get_ctx(device, &c));
+    CU(cudaSetDevice(c->dev));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return OXG_OK;
+}
+
+oxg_status oxg_ipc_close(int device, void *d_ptr) {
+    DeviceCtx *c;
+    TRY(get_ctx(device, &c));
+    CU(cudaSetDevice(c->dev));
+    CU(cudaIpcCloseMemHandle(d_ptr));
     return OXG_OK;
 }
 

@@ -73,6 +73,13 @@ struct ConsumeParams {
     uint64_t *route_out[kMaxRanks];
     uint64_t *route_counts;
     uint64_t route_cap;
+    // hashes received from other ranks (previous chunk), absorbed by the same launch:
+    // segment i holds absorb_n[i] hashes; blocks of kWarpTile hashes are numbered across
+    // segments, segment i starting at block absorb_first[i]
+    const uint64_t *absorb_ptr[kMaxRanks];
+    uint64_t absorb_n[kMaxRanks];
+    uint64_t absorb_first[kMaxRanks + 1];
+    int n_absorb;
 };
 
 __global__ void tile_first_kernel(const uint64_t *__restrict__ offsets, uint64_t n_off,
@@ -218,11 +225,40 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
     uint64_t n_counted = 0;
     uint64_t first_bad = ~0ULL;
 
-    for (;;) {
+    uint64_t n_absorbed = 0;
+    bool tiles_left = true;
+    bool absorb_left = MODE == kModeRoute && p.n_absorb > 0;
+    while (tiles_left || absorb_left) {
+        if (MODE == kModeRoute && absorb_left) {
+            // one block of hashes that other ranks routed here (they were stored into this
+            // GPU's receive regions by the peers' previous launch)
+            uint64_t b = 0;
+            if (lane == 0) b = atomicAdd((unsigned long long *)&p.table.ctrl->absorb_counter, 1ULL);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b >= p.absorb_first[p.n_absorb]) {
+                absorb_left = false;
+            } else {
+                int seg = 0;
+                while (b >= p.absorb_first[seg + 1]) ++seg;
+                const uint64_t off = (b - p.absorb_first[seg]) * kWarpTile;
+                uint64_t h[kWPT];
+#pragma unroll
+                for (int j = 0; j < kWPT; ++j) {
+                    const uint64_t i = off + j * 32 + lane;
+                    h[j] = i < p.absorb_n[seg] ? __ldcs(p.absorb_ptr[seg] + i) : 0;
+                }
+                const bool full = __ldcg(&p.table.ctrl->size) >= p.table.limit;
+                uint32_t created = 0;
+                count_hashes8(p.table, h, full, s_queue_all[warp], n_absorbed, created);
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
+                if (lane == 0 && tot) atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
+            }
+        }
+        if (!tiles_left) continue;
         uint64_t t = 0;
         if (lane == 0) t = atomicAdd((unsigned long long *)&p.table.ctrl->tile_counter, 1ULL);
         t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= p.n_tiles) break;
+        if (t >= p.n_tiles) { tiles_left = false; continue; }
         const uint64_t w0 = p.tile_base + t * kWarpTile;
 
         if (lane < NE) s_end[lane] = 0;
@@ -344,6 +380,11 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
         for (int o = 16; o; o >>= 1) n_counted += __shfl_xor_sync(0xffffffffu, n_counted, o);
         if (lane == 0 && n_counted)
             atomicAdd((unsigned long long *)&p.table.ctrl->counted, (unsigned long long)n_counted);
+        if (MODE == kModeRoute) {
+            for (int o = 16; o; o >>= 1) n_absorbed += __shfl_xor_sync(0xffffffffu, n_absorbed, o);
+            if (lane == 0 && n_absorbed)
+                atomicAdd((unsigned long long *)&p.table.ctrl->absorbed, (unsigned long long)n_absorbed);
+        }
     }
 }
 

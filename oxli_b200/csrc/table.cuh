@@ -25,6 +25,8 @@ struct Ctrl {              // lives in device memory, mirrored to pinned host me
     uint64_t counted;      // k-mers counted by the running consume launch
     uint64_t overflow;     // entries appended to the overflow list
     uint64_t tile_counter; // dynamic tile scheduler of the running consume launch
+    uint64_t absorb_counter; // same, for blocks of received hashes (sharded route launches)
+    uint64_t absorbed;     // received hashes counted by the running launch
     uint64_t first_bad;    // error-mode scan: smallest bad window start
     uint64_t scratch[10];  // per-op outputs (stats, set sizes, ...)
 };

@@ -48,9 +48,17 @@ class RouteResult:
 
 class CudaShardEngine:
     """Per-rank compute on one GPU through the C ABI (no torch in the library;
-    torch only owns the exchange buffers and the process group)."""
+    torch only owns the process group and, in "nccl" mode, the exchange buffers).
 
-    def __init__(self, ksize: int, rank: int, world: int, device: int, capacity_hint: int = 0, out_capacity: int = 0):
+    exchange="p2p" (default): every rank owns a receive buffer with one region per
+    source rank, exported over CUDA IPC; the route kernel of rank s stores the hashes
+    owned by rank d straight into region s of d's buffer over NVLink, so there is no
+    separate bulk exchange -- only the list lengths travel through the process group.
+    exchange="nccl": outgoing lists are staged locally and exchanged with grouped
+    send/recv (the plain-library baseline, also what the CPU tests model)."""
+
+    def __init__(self, ksize: int, rank: int, world: int, device: int, capacity_hint: int = 0,
+                 out_capacity: int = 0, exchange: str = "p2p"):
         import torch
 
         from . import _capi as capi
@@ -60,9 +68,14 @@ class CudaShardEngine:
         self.table = capi.Table(ksize, device=device, capacity_hint=capacity_hint)
         self.ksize = ksize
         self.out_capacity = out_capacity
+        self.exchange = exchange
         self._out = None
+        self._cap = 0
+        self._recv_base = 0          # p2p: this rank's receive buffer (world regions of _cap entries)
+        self._peer_bases = None      # p2p: imported receive buffers of the peers
         self._counts = torch.zeros(world, dtype=torch.int64, device=f"cuda:{device}")
 
+    # -- nccl mode ------------------------------------------------------------------
     def _ensure_out(self, cap: int):
         torch = self.torch
         if self._out is None or self._out[0].numel() < cap:
@@ -70,22 +83,70 @@ class CudaShardEngine:
                          for r in range(self.world)]
         return self._out
 
-    def route(self, d_bases: int, d_offsets: int, n_reads: int, total_bases: int) -> RouteResult:
+    # -- p2p mode -------------------------------------------------------------------
+    def setup_p2p(self, dist, group, cap: int):
+        """(Re)allocate the receive buffer for `cap` hashes per source and swap IPC handles."""
+        capi = self.capi
+        if self._peer_bases is not None and cap <= self._cap:
+            return
+        self.close_p2p()
+        self._cap = cap
+        self._recv_base = capi.device_alloc(2 * self.world * cap * 8, self.device)  # two parities x world regions
+        handles = [None] * self.world
+        dist.all_gather_object(handles, capi.ipc_export(self._recv_base, self.device), group=group)
+        self._peer_bases = [capi.ipc_import(h, self.device) if r != self.rank else self._recv_base
+                            for r, h in enumerate(handles)]
+        dist.barrier(group=group)
+
+    def close_p2p(self):
+        if self._peer_bases is not None:
+            for r, p in enumerate(self._peer_bases):
+                if r != self.rank:
+                    self.capi.ipc_close(p, self.device)
+            self.capi.device_free(self._recv_base, self.device)
+            self._peer_bases, self._recv_base, self._cap = None, 0, 0
+
+    def capacity_for(self, total_bases: int) -> int:
+        n_win = max(total_bases - self.ksize + 1, 0)
+        return self.out_capacity or int(n_win / self.world * 1.25) + (1 << 16)
+
+    def route(self, d_bases: int, d_offsets: int, n_reads: int, total_bases: int, base_lo: int = 0,
+              base_hi: int | None = None, parity: int = 0, absorb: list[tuple[int, int]] | None = None) -> RouteResult:
+        """Hash the reads in bytes [base_lo, base_hi) of the batch.  p2p mode: remote hashes
+        land in region (parity, self.rank) of each owner's receive buffer.  `absorb` =
+        [(device pointer, n)] received hash lists the same launch counts as well."""
         import ctypes as C
 
         capi = self.capi
-        n_win = max(total_bases - self.ksize + 1, 0)
-        cap = self.out_capacity or int(n_win / self.world * 1.25) + (1 << 16)
-        out = self._ensure_out(cap)
-        ptrs = (C.c_void_p * self.world)(*[t.data_ptr() for t in out])
+        base_hi = total_bases if base_hi is None else base_hi
+        if self.exchange == "p2p":
+            cap = self._cap
+            ptrs = (C.c_void_p * self.world)(*[self._peer_bases[d] + self.region_offset(parity, self.rank)
+                                               for d in range(self.world)])
+            out = None
+        else:
+            cap = self.capacity_for(base_hi - base_lo)
+            out = self._ensure_out(cap)
+            ptrs = (C.c_void_p * self.world)(*[t.data_ptr() for t in out])
+        absorb = [(p, n) for p, n in (absorb or []) if n]
+        a_ptrs = (C.c_void_p * max(len(absorb), 1))(*[p for p, _ in absorb])
+        a_n = (C.c_uint64 * max(len(absorb), 1))(*[n for _, n in absorb])
         host_counts = (C.c_uint64 * self.world)()
-        local = C.c_uint64()
+        local, absorbed = C.c_uint64(), C.c_uint64()
         self.torch.cuda.synchronize(self.device)
-        capi.check(capi.lib.oxg_route_batch_device(self.table.handle, d_bases, d_offsets, n_reads, total_bases,
+        capi.check(capi.lib.oxg_route_batch_device(self.table.handle, d_bases, d_offsets, n_reads, base_lo, base_hi,
                                                    self.world, self.rank, ptrs, cap, self._counts.data_ptr(),
-                                                   host_counts, C.byref(local)))
+                                                   host_counts, C.byref(local), len(absorb), a_ptrs, a_n,
+                                                   C.byref(absorbed)))
+        self.last_absorbed = int(absorbed.value)
+        if out is None:
+            return RouteResult(int(local.value), [int(host_counts[r]) if r != self.rank else 0 for r in range(self.world)])
         return RouteResult(int(local.value), [out[r][: int(host_counts[r])] if r != self.rank else out[r][:0]
                                               for r in range(self.world)])
+
+    def region_offset(self, parity: int, source: int) -> int:
+        """Byte offset of receive region (parity, source) inside a rank's receive buffer."""
+        return (parity * self.world + source) * self._cap * 8
 
     def new_buffer(self, n: int):
         return self.torch.empty(n, dtype=self.torch.int64, device=f"cuda:{self.device}")
@@ -95,6 +156,15 @@ class CudaShardEngine:
             return 0
         self.torch.cuda.synchronize(self.device)
         return self.table.count_hashes_device(hashes.data_ptr(), hashes.numel(), skip_zero=False)
+
+    def region_ptr(self, parity: int, source: int) -> int:
+        return self._recv_base + self.region_offset(parity, source)
+
+    def count_region(self, parity: int, source: int, n: int) -> int:
+        """p2p: absorb the first n hashes that rank `source` stored into this rank's buffer."""
+        if n == 0:
+            return 0
+        return self.table.count_hashes_device(self.region_ptr(parity, source), n, skip_zero=False)
 
     def clear(self):
         self.table.clear()
@@ -167,8 +237,65 @@ class ShardedCounter:
         for r in range(self.world):
             recv_n[r] = rows[r][self.rank]
 
-    def consume_device(self, d_bases: int, d_offsets: int, n_reads: int, total_bases: int) -> int:
-        return self.consume_routed(self.engine.route(d_bases, d_offsets, n_reads, total_bases))
+    def consume_device(self, d_bases: int, d_offsets: int, n_reads: int, total_bases: int,
+                       h_offsets: np.ndarray | None = None, chunks: int = 8) -> int:
+        """Count a device-resident batch of this rank's reads into the sharded table.
+        Returns the number of k-mers this rank's shard absorbed (own + received)."""
+        eng = self.engine
+        if getattr(eng, "exchange", "nccl") != "p2p":
+            return self.consume_routed(eng.route(d_bases, d_offsets, n_reads, total_bases))
+        # Fused exchange, pipelined over chunks of reads.  The route launch of chunk c
+        #   - stores the hashes owned elsewhere straight into the owners' receive regions
+        #     (parity c&1) over NVLink,
+        #   - counts the hashes it owns, and
+        #   - absorbs what the peers delivered during chunk c-1 (parity (c-1)&1),
+        # so hashing, remote stores and the counting of received hashes overlap inside one
+        # kernel.  Only the list lengths go through the process group; that all-to-all is
+        # also the "everyone finished writing chunk c" barrier, and because a rank enters
+        # it only after its own route(c) -- which absorbed chunk c-1 -- returned, parity
+        # c&1 is free again when any rank starts chunk c+2.
+        import torch
+
+        dist = self.dist
+        if h_offsets is None:
+            h_offsets = np.empty(n_reads + 1, dtype=np.uint64)
+            eng.capi.d2h(h_offsets, d_offsets, eng.device)
+        chunks = max(1, min(chunks, n_reads))
+        # read boundaries whose byte offset keeps the 16-byte alignment of tile bases
+        cuts = [0]
+        for c in range(1, chunks):
+            r = n_reads * c // chunks
+            while r < n_reads and int(h_offsets[r]) % 16:
+                r += 1
+            if r > cuts[-1] and r < n_reads:
+                cuts.append(r)
+        cuts.append(n_reads)
+        biggest = max(int(h_offsets[cuts[i + 1]] - h_offsets[cuts[i]]) for i in range(len(cuts) - 1))
+        cap = torch.tensor([eng.capacity_for(biggest), len(cuts) - 1], dtype=torch.int64, device=f"cuda:{eng.device}")
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
+        eng.setup_p2p(dist, self.group, int(cap[0].item()))
+        n_rounds = int(cap[1].item())  # ranks may cut differently; everyone runs the same number of rounds
+
+        absorbed, pending, sent, received = 0, [], 0, 0
+        for c in range(n_rounds):
+            if c < len(cuts) - 1:
+                lo, hi = int(h_offsets[cuts[c]]), int(h_offsets[cuts[c + 1]])
+            else:
+                lo = hi = int(h_offsets[n_reads])
+            routed = eng.route(d_bases, d_offsets, n_reads, total_bases, lo, hi, parity=c & 1, absorb=pending)
+            absorbed += routed.local_counted + eng.last_absorbed
+            send_n = torch.tensor(routed.outgoing, dtype=torch.int64, device=f"cuda:{eng.device}")
+            recv_n = torch.empty_like(send_n)
+            dist.all_to_all_single(recv_n, send_n, group=self.group)
+            recv = recv_n.cpu().tolist()
+            pending = [(eng.region_ptr(c & 1, src), int(recv[src])) for src in range(self.world) if src != self.rank]
+            sent += int(sum(routed.outgoing)); received += int(sum(recv))
+        for ptr, n in pending:  # what arrived during the last round
+            if n:
+                absorbed += eng.table.count_hashes_device(ptr, n, skip_zero=False)
+        dist.barrier(group=self.group)  # nobody re-enters and overwrites regions still being read
+        self.last = {"sent": sent, "received": received, "rounds": n_rounds}
+        return absorbed
 
     # -- reductions ------------------------------------------------------------------
     def _reduce(self, values: list[int], op) -> list[int]:
@@ -238,12 +365,16 @@ def run_sharded_bench(a, rank: int, world: int, local: int) -> None:
     d_offs = capi.device_alloc((n + 1) * 8, local)
     capi.synth_reads_device(d_bases, n, L, a.genome, SEED, first_read=rank * n, device=local)
     capi.h2d(d_offs, np.arange(n + 1, dtype=np.uint64) * np.uint64(L), local)
-    engine = CudaShardEngine(k, rank, world, local, capacity_hint=(a.table_hint or a.genome) // world + 1024)
+    engine = CudaShardEngine(k, rank, world, local, capacity_hint=(a.table_hint or a.genome) // world + 1024,
+                             exchange=os.environ.get("OXLI_B200_EXCHANGE", "p2p"))
     sc = ShardedCounter(engine)
+
+    h_offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
+    n_chunks = int(os.environ.get("OXLI_B200_CHUNKS", "8"))
 
     def step():
         engine.clear()
-        return sc.consume_device(d_bases, d_offs, n, total_bases)
+        return sc.consume_device(d_bases, d_offs, n, total_bases, h_offsets=h_offs, chunks=n_chunks)
 
     absorbed = 0
     for _ in range(a.warmup):
@@ -277,7 +408,8 @@ def run_sharded_bench(a, rank: int, world: int, local: int) -> None:
             "data": "synthetic",
             "config": {"workload": workload_name(a, world), "ksize": k, "read_len": L, "reads_per_gpu": n,
                        "genome_len": a.genome, "distinct_kmers": st["len"], "sharding": f"hash-high-bits x{world}",
-                       "exchange": "all-to-all of u64 hashes (grouped NCCL send/recv over NVLink)",
+                       "exchange": ("route kernel stores remote hashes into the owner's HBM over NVLink (CUDA IPC peer memory)"
+                                    if engine.exchange == "p2p" else "all-to-all of u64 hashes (grouped NCCL send/recv over NVLink)"),
                        "l2_policy": "inputs (1.5 GB of reads per GPU per step) far exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                          "frac": achieved / (peak * world), "traffic": None, "alg_bytes_per_kmer": balg,

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, k, out_dir):
+def _worker(rank, world, port, k, out_dir, exchange):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch
@@ -30,7 +30,7 @@ def _worker(rank, world, port, k, out_dir):
         d_offs = capi.device_alloc((n + 1) * 8, rank)
         capi.synth_reads_device(d_bases, n, L, G, seed=77, first_read=rank * n, sub_ppm=5000, n_ppm=800, device=rank)
         capi.h2d(d_offs, uniform_offsets(n, L), rank)
-        eng = CudaShardEngine(k, rank, world, rank, capacity_hint=G // world)
+        eng = CudaShardEngine(k, rank, world, rank, capacity_hint=G // world, exchange=exchange)
         sc = ShardedCounter(eng)
         absorbed = sc.consume_device(d_bases, d_offs, n, n * L)
         absorbed += sc.consume_device(d_bases, d_offs, n, n * L)  # twice: counts double
@@ -53,7 +53,7 @@ def _worker(rank, world, port, k, out_dir):
         assert np.array_equal(allk[order], tk) and np.array_equal(allv[order], tv)
         assert sc.stats() == {"len": len(truth), "sum": truth.sum_counts, "min": truth.min, "max": truth.max}
         assert sc.histo(zero=False) == truth.histo(zero=False)
-        other = ShardedCounter(CudaShardEngine(k, rank, world, rank))
+        other = ShardedCounter(CudaShardEngine(k, rank, world, rank, exchange=exchange))
         other.consume_device(d_bases, d_offs, n // 2, (n // 2) * L)
         t2 = OracleTable(k)
         for r in range(world):
@@ -72,13 +72,13 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("k", [21, 31])
-def test_two_gpu_sharded_counting(tmp_path, k):
+@pytest.mark.parametrize("k,exchange", [(21, "p2p"), (31, "p2p"), (31, "nccl")])
+def test_two_gpu_sharded_counting(tmp_path, k, exchange):
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
 
-    mp.spawn(_worker, args=(2, _free_port(), k, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), k, str(tmp_path), exchange), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
