@@ -237,10 +237,26 @@ class ShardedCounter:
         for r in range(self.world):
             recv_n[r] = rows[r][self.rank]
 
+    @staticmethod
+    def plan_chunks(h_offsets: np.ndarray, n_reads: int, chunks: int) -> list[int]:
+        """Read indices at which a batch is cut: byte offsets stay 16-byte aligned."""
+        chunks = max(1, min(chunks, n_reads))
+        cuts = [0]
+        for c in range(1, chunks):
+            r = n_reads * c // chunks
+            while r < n_reads and int(h_offsets[r]) % 16:
+                r += 1
+            if r > cuts[-1] and r < n_reads:
+                cuts.append(r)
+        cuts.append(n_reads)
+        return cuts
+
     def consume_device(self, d_bases: int, d_offsets: int, n_reads: int, total_bases: int,
-                       h_offsets: np.ndarray | None = None, chunks: int = 8) -> int:
+                       h_offsets: np.ndarray | None = None, chunks: int = 8, chunk_ready=None) -> int:
         """Count a device-resident batch of this rank's reads into the sharded table.
-        Returns the number of k-mers this rank's shard absorbed (own + received)."""
+        Returns the number of k-mers this rank's shard absorbed (own + received).
+        chunk_ready(c), if given, is called before chunk c is touched (lets a caller
+        stream the bases in behind the pipeline)."""
         eng = self.engine
         if getattr(eng, "exchange", "nccl") != "p2p":
             return self.consume_routed(eng.route(d_bases, d_offsets, n_reads, total_bases))
@@ -260,16 +276,7 @@ class ShardedCounter:
         if h_offsets is None:
             h_offsets = np.empty(n_reads + 1, dtype=np.uint64)
             eng.capi.d2h(h_offsets, d_offsets, eng.device)
-        chunks = max(1, min(chunks, n_reads))
-        # read boundaries whose byte offset keeps the 16-byte alignment of tile bases
-        cuts = [0]
-        for c in range(1, chunks):
-            r = n_reads * c // chunks
-            while r < n_reads and int(h_offsets[r]) % 16:
-                r += 1
-            if r > cuts[-1] and r < n_reads:
-                cuts.append(r)
-        cuts.append(n_reads)
+        cuts = self.plan_chunks(h_offsets, n_reads, chunks)
         biggest = max(int(h_offsets[cuts[i + 1]] - h_offsets[cuts[i]]) for i in range(len(cuts) - 1))
         cap = torch.tensor([eng.capacity_for(biggest), len(cuts) - 1], dtype=torch.int64, device=f"cuda:{eng.device}")
         dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
@@ -280,6 +287,8 @@ class ShardedCounter:
         for c in range(n_rounds):
             if c < len(cuts) - 1:
                 lo, hi = int(h_offsets[cuts[c]]), int(h_offsets[cuts[c + 1]])
+                if chunk_ready is not None:
+                    chunk_ready(c)
             else:
                 lo = hi = int(h_offsets[n_reads])
             routed = eng.route(d_bases, d_offsets, n_reads, total_bases, lo, hi, parity=c & 1, absorb=pending)
@@ -361,20 +370,32 @@ def run_sharded_bench(a, rank: int, world: int, local: int) -> None:
     n, L, k = a.reads, a.read_len, a.ksize
     total_bases = n * L
     kmers_per_rank = n * (L - k + 1)
-    d_bases = capi.device_alloc(total_bases + 64, local)
+    bases_t = torch.empty(total_bases + 64, dtype=torch.uint8, device=f"cuda:{local}")
+    d_bases = bases_t.data_ptr()
     d_offs = capi.device_alloc((n + 1) * 8, local)
     capi.synth_reads_device(d_bases, n, L, a.genome, SEED, first_read=rank * n, device=local)
-    capi.h2d(d_offs, np.arange(n + 1, dtype=np.uint64) * np.uint64(L), local)
+    h_offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
+    capi.h2d(d_offs, h_offs, local)
     engine = CudaShardEngine(k, rank, world, local, capacity_hint=(a.table_hint or a.genome) // world + 1024,
                              exchange=os.environ.get("OXLI_B200_EXCHANGE", "p2p"))
     sc = ShardedCounter(engine)
-
-    h_offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
     n_chunks = int(os.environ.get("OXLI_B200_CHUNKS", "8"))
 
-    def step():
+    def step(chunk_ready=None):
         engine.clear()
-        return sc.consume_device(d_bases, d_offs, n, total_bases, h_offsets=h_offs, chunks=n_chunks)
+        return sc.consume_device(d_bases, d_offs, n, total_bases, h_offsets=h_offs, chunks=n_chunks,
+                                 chunk_ready=chunk_ready)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        out = 0
+        for _ in range(steps):
+            out = fn()
+        torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+        return float(t.item()), out
 
     absorbed = 0
     for _ in range(a.warmup):
@@ -382,16 +403,37 @@ def run_sharded_bench(a, rank: int, world: int, local: int) -> None:
     torch.cuda.synchronize(); dist.barrier()
     launches0 = int(capi.lib.oxg_launch_count())
     with ClockSampler(local) as clocks:
-        torch.cuda.synchronize(); dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(a.steps):
-            absorbed = step()
-        torch.cuda.synchronize(); dist.barrier()
-        dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+        dt, absorbed = timed(step, a.steps)
     launches = int(capi.lib.oxg_launch_count()) - launches0
+
+    # end to end: every rank's reads start in pinned host memory; each step streams them to the
+    # GPU chunk by chunk on a copy stream while the pipeline works on the chunks already there
+    e2e = None
+    if not a.no_e2e:
+        h_bases = torch.empty(total_bases, dtype=torch.uint8).pin_memory()
+        h_bases.copy_(bases_t[:total_bases])
+        copy_stream = torch.cuda.Stream(device=local)
+        cuts = ShardedCounter.plan_chunks(h_offs, n, n_chunks)
+
+        def step_e2e():
+            events = []
+            with torch.cuda.stream(copy_stream):
+                for c in range(len(cuts) - 1):
+                    lo, hi = int(h_offs[cuts[c]]), int(h_offs[cuts[c + 1]])
+                    bases_t[lo:hi].copy_(h_bases[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(copy_stream); events.append(ev)
+            got = step(chunk_ready=lambda c: events[c].synchronize())
+            return got + 0 * len(sc)  # device -> host read of the result
+
+        step_e2e()
+        dt2, absorbed2 = timed(step_e2e, a.steps)
+        e2e = {"value": kmers_per_rank * world / (dt2 / a.steps), "unit": UNIT,
+               "h2d_bytes_per_step": int(world * (total_bases + (n + 1) * 0 + 16 * n_chunks * world)),
+               "d2h_bytes_per_step": int(world * (n_chunks * (8 * world + 128) + 64)),
+               "ms_per_step": 1e3 * dt2 / a.steps,
+               "timing": "barrier + cuda sync both sides, max over ranks; pinned host -> chunked async H2D inside the step"}
+        assert absorbed2 == absorbed
+
     tot = torch.tensor([absorbed, launches], dtype=torch.int64, device=f"cuda:{local}")
     dist.all_reduce(tot)
     st = sc.stats()
@@ -408,13 +450,15 @@ def run_sharded_bench(a, rank: int, world: int, local: int) -> None:
             "data": "synthetic",
             "config": {"workload": workload_name(a, world), "ksize": k, "read_len": L, "reads_per_gpu": n,
                        "genome_len": a.genome, "distinct_kmers": st["len"], "sharding": f"hash-high-bits x{world}",
-                       "exchange": ("route kernel stores remote hashes into the owner's HBM over NVLink (CUDA IPC peer memory)"
+                       "exchange": ("route kernel stores remote hashes into the owner's HBM over NVLink (CUDA IPC peer memory), "
+                                    f"{n_chunks}-chunk pipeline with fused absorb"
                                     if engine.exchange == "p2p" else "all-to-all of u64 hashes (grouped NCCL send/recv over NVLink)"),
                        "l2_policy": "inputs (1.5 GB of reads per GPU per step) far exceed the 126 MB L2; no flush needed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
                          "frac": achieved / (peak * world), "traffic": None, "alg_bytes_per_kmer": balg,
-                         "peak_source": peak_src + f" x {world} GPUs", "scope": "whole step, all ranks"},
-            "e2e": None, "gpu_launches": int(tot[1]), "timing": "barrier + cuda sync both sides, max over ranks",
+                         "peak_source": peak_src + f" x {world} GPUs", "scope": "whole step, all ranks",
+                         "kernel": f"consume_kernel<{k},route>"},
+            "e2e": e2e, "gpu_launches": int(tot[1]), "timing": "barrier + cuda sync both sides, max over ranks",
             "exchange_last_step_rank0": sc.last, "clocks": clocks.summary(),
         }), flush=True)
     dist.destroy_process_group()

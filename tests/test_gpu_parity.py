@@ -261,6 +261,42 @@ def test_device_resident_consume_and_generator(capi):
         capi.device_free(d_offs)
 
 
+def test_c3_shaped_k21_errors_and_ns(capi):
+    # BASELINE.json configs[2] in miniature: k=21, 1 % substitutions, 0.1 % N, both bad-k-mer modes
+    k, L, n, G = 21, 150, 300_000, 2_000_000
+    bases = synth_reads(n, L, G, seed=0xC30001, sub_ppm=10000, n_ppm=1000)
+    offs = uniform_offsets(n, L)
+    for skip in (True, False):
+        ora = OracleTable(k)
+        want = ora.consume_batch(bases, offs, skip, nthreads=8 if skip else 1)
+        t = capi.Table(k)
+        st, total, er, ep = t.consume_batch(bases, offs, skip)
+        assert (total, er, ep) == want and st == (0 if er < 0 else capi.ERR_BAD_KMER)
+        assert_same_table(t, ora)
+        if skip:
+            assert t.histo() == ora.histo(zero=False)
+            s = t.stats()
+            assert (s["len"], s["sum"], s["min"], s["max"]) == (len(ora), ora.sum_counts, ora.min, ora.max)
+
+
+def test_long_reads_k21(capi):
+    # configs[4]: 10-kbp reads (intra-read tiling: one read spans ~40 warp tiles)
+    k, L, n, G = 21, 10_000, 1500, 400_000
+    bases = synth_reads(n, L, G, seed=0xC50001, sub_ppm=3000, n_ppm=200)
+    offs = uniform_offsets(n, L)
+    ora = OracleTable(k)
+    want, _, _ = ora.consume_batch(bases, offs, True, nthreads=8)
+    t = capi.Table(k)
+    st, total, _, _ = t.consume_batch(bases, offs)
+    assert total == want
+    assert_same_table(t, ora)
+    # jaccard against a table built from the first half of the reads (key sets nest)
+    half, oh = capi.Table(k), OracleTable(k)
+    half.consume_batch(bases[: n // 2 * L], offs[: n // 2 + 1])
+    oh.consume_batch(bases[: n // 2 * L], offs[: n // 2 + 1], True, nthreads=8)
+    assert t.setop_sizes(half) == ora.setop_sizes(oh) and t.jaccard(half) == ora.jaccard(oh)
+
+
 # ------------------------------------------------------------------ table ops
 
 def test_hash_level_ops(capi):
