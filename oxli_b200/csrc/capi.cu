@@ -150,11 +150,30 @@ int grid_for(const DeviceCtx *c, uint64_t items, int threads, int per_sm) {
     return (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)c->sms * per_sm));
 }
 
+// Capacity policy.  Displaced keys are what slows the probe loop down
+// (profiles/r1_microbench_probe_slow_path.txt: 16 % home-bucket misses at load
+// 0.6 cut a 62 G keys/s loop to 23-35 G keys/s; at load 0.15 it runs at 66), so
+// a table that is small anyway is kept sparse: up to kSparseBytes the target
+// load is <= 0.3, beyond that memory and L2 footprint win and it may fill to 0.7.
+constexpr uint64_t kSparseBytes = 128ull << 20;
+uint64_t capacity_for_keys(uint64_t keys);
+bool over_loaded(uint64_t size, uint64_t cap) {
+    if (cap * 16 < kSparseBytes) return size * 10 > cap * 3;
+    return size * 10 > cap * 7;
+}
+
 uint64_t pow2_at_least(uint64_t x) {
     uint64_t c = kMinCap;
     while (c < x) c <<= 1;
     return c;
 }
+
+uint64_t capacity_for_keys(uint64_t keys) {
+    uint64_t cap = pow2_at_least(keys + keys / 2 + 1);                  // <= 67 % load
+    while (cap * 16 < kSparseBytes && keys * 10 > cap * 3) cap <<= 1;   // sparse while it is cheap
+    return cap;
+}
+
 
 }  // namespace
 
@@ -213,7 +232,7 @@ oxg_status alloc_slots(DeviceCtx *c, uint64_t cap, ulonglong2 **out) {
 
 // grow (or rebuild at the same size) so that `keys` distinct keys sit at <= 50 % load
 oxg_status grow_to_fit(oxg_table *t, uint64_t keys) {
-    uint64_t want = pow2_at_least(keys * 2);
+    uint64_t want = std::max(capacity_for_keys(keys), pow2_at_least(keys * 2));
     if (want <= t->cap) return OXG_OK;
     DeviceCtx *c = t->ctx;
     ulonglong2 *fresh = nullptr;
@@ -289,7 +308,7 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
         if (mode == kModeCount) {
             const uint64_t span = hi - lo;
             if (span <= kSmallBatch) TRY(reserve_keys(t, span));
-            else if (t->size * 10 > t->cap * 7) TRY(grow_to_fit(t, t->size));  // > 70 % load: double
+            else if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
             TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, span));
             TRY(zero_ctrl_fields(t, kFieldCounted, 5));  // counted, overflow, tile_counter, absorb_*
         } else {
@@ -402,7 +421,7 @@ oxg_status oxg_table_create(int device, uint32_t ksize, uint64_t capacity_hint, 
     CU(cudaSetDevice(c->dev));
     auto t = std::make_unique<oxg_table>();
     t->ctx = c; t->k = ksize;
-    t->cap = pow2_at_least(capacity_hint + capacity_hint / 2 + 1);  // <= 67 % load at the hint
+    t->cap = capacity_for_keys(capacity_hint);
     CU(cudaMalloc(&t->d_ctrl, sizeof(Ctrl)));
     CU(cudaMemsetAsync(t->d_ctrl, 0, sizeof(Ctrl), c->stream));
     CU(cudaMallocHost(&t->h_ctrl, sizeof(Ctrl)));
@@ -671,7 +690,7 @@ static oxg_status count_list_device(oxg_table *t, const uint64_t *d_hashes, uint
         const bool optimistic = m > kSmallBatch;
         if (!optimistic) TRY(reserve_keys(t, m));
         else {
-            if (t->size * 10 > t->cap * 7) TRY(grow_to_fit(t, t->size));
+            if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
             TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, m));
         }
         TRY(zero_ctrl_fields(t, kFieldCounted, 5));
@@ -1129,7 +1148,7 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
         const uint32_t tw = tile_width(t->k);
         const uint64_t n_tiles = hi > tile_base ? (hi - tile_base + tw - 1) / tw : 0;
         TRY(ensure_dev(&c->d_tile_first, &c->tile_first_cap, std::max<uint64_t>(n_tiles, 1)));
-        if (t->size * 10 > t->cap * 7) TRY(grow_to_fit(t, t->size));
+        if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
         TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, (hi > lo ? hi - lo : 0) + (first ? absorb_total : 0) + 1));
         TRY(zero_ctrl_fields(t, kFieldCounted, 5));  // counted, overflow, tile_counter, absorb_counter, absorbed
         ConsumeParams p{};

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
     __shared__ __align__(8) uint16_t s_bad_all[kWarps][NV + 6 + ((NV + 6) & 1) + 2];
     __shared__ __align__(8) uint32_t s_end_all[kWarps][NE + (NE & 1)];
     __shared__ __align__(8) uint64_t s_queue_all[kCounts ? kWarps : 1][kCounts ? kWPT * 32 + kWPT * 4 : 1];  // keys + resume bytes
-    __shared__ __align__(8) uint64_t s_route_all[MODE == kModeRoute ? kWarps : 1][MODE == kModeRoute ? kMaxRanks / 2 + kMaxRanks : 1];
+    __shared__ __align__(8) uint64_t s_route_all[MODE == kModeRoute ? kWarps : 1][MODE == kModeRoute ? 2 * kMaxRanks + 1 + kWarpTile / 8 : 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *s_fw = s_fw_all[warp], *s_rc = s_rc_all[warp];
@@ -336,11 +336,18 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
             } else if (kCounts) {
                 uint32_t created = 0;
                 if (MODE == kModeRoute) {
-                    // Hashes owned by another rank go to that rank's outgoing list.  Positions
-                    // are handed out per warp tile: shared-memory counters rank the tile's
-                    // hashes per owner, then ONE global atomic per owner reserves the run.
-                    uint32_t *s_rcnt = reinterpret_cast<uint32_t *>(s_route_all[warp]);
-                    uint64_t *s_rbase = s_route_all[warp] + kMaxRanks / 2;
+                    // Hashes owned by another rank go to that rank's outgoing list -- which may
+                    // live in the owner's HBM (peer memory): then these stores ARE the exchange.
+                    // Per warp tile: shared-memory counters rank the hashes per owner, one global
+                    // atomic per owner reserves the run, the hashes are gathered per owner in
+                    // shared memory and written out by consecutive lanes, so every store
+                    // instruction covers up to 256 contiguous bytes per owner (full-size NVLink
+                    // packets instead of scattered 8-byte writes).
+                    uint32_t *s_rcnt = reinterpret_cast<uint32_t *>(s_route_all[warp]);        // [kMaxRanks]
+                    uint32_t *s_rpre = s_rcnt + kMaxRanks;                                     // [kMaxRanks + 1]
+                    uint64_t *s_rbase = s_route_all[warp] + kMaxRanks + 1;                     // [kMaxRanks]
+                    uint64_t *s_stage = s_queue_all[warp];                                     // queue is idle now
+                    uint8_t *s_owner = reinterpret_cast<uint8_t *>(s_route_all[warp] + 2 * kMaxRanks + 1);  // [kWarpTile]
                     if (lane < kMaxRanks) s_rcnt[lane] = 0;
                     __syncwarp();
                     uint32_t slot_in_run[kWPT];
@@ -352,15 +359,28 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
                     __syncwarp();
                     if (lane < p.n_ranks && s_rcnt[lane])
                         s_rbase[lane] = atomicAdd((unsigned long long *)&p.route_counts[lane], (unsigned long long)s_rcnt[lane]);
+                    if (lane == 0) {
+                        uint32_t run = 0;
+                        for (int o = 0; o < p.n_ranks; ++o) { s_rpre[o] = run; run += s_rcnt[o]; }
+                        s_rpre[p.n_ranks] = run;
+                    }
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < kWPT; ++j) {
                         const int owner = (int)(h[j] >> p.owner_shift);
                         if (h[j] != 0 && owner != p.self_rank) {
-                            const uint64_t at = s_rbase[owner] + slot_in_run[j];
-                            if (at < p.route_cap) p.route_out[owner][at] = h[j];
+                            const uint32_t at = s_rpre[owner] + slot_in_run[j];
+                            s_stage[at] = h[j];
+                            s_owner[at] = (uint8_t)owner;
                             h[j] = 0;
                         }
+                    }
+                    __syncwarp();
+                    const uint32_t n_out = s_rpre[p.n_ranks];
+                    for (uint32_t i = lane; i < n_out; i += 32) {
+                        const int owner = s_owner[i];
+                        const uint64_t at = s_rbase[owner] + (i - s_rpre[owner]);
+                        if (at < p.route_cap) p.route_out[owner][at] = s_stage[i];
                     }
                     __syncwarp();
                 }
