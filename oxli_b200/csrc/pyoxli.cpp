@@ -13,6 +13,9 @@
 //   KmerCountTable(ksize, store_kmers=False, *, device=0, capacity_hint=0)
 //   consume_many(seqs, skip_bad_kmers=True)      one GPU batch for many reads
 //   consume_buffer(bases, offsets, skip_bad_kmers=True)   CSR batch, zero-copy from buffers
+//   consume_file(path, skip_bad_kmers=True)      FASTA/FASTQ (plain or gzip) parsed into pinned
+//                                                 batches -- the loop the reference leaves to
+//                                                 screed (README.md:89-98)
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -314,6 +317,103 @@ struct Table {
     }
 };
 
+// FASTA / FASTQ reader feeding pinned CSR batches to the GPU.  Records are what
+// screed would hand to consume(): FASTA sequence lines joined, FASTQ 4-line records.
+struct PinnedBatch {
+    uint8_t *bases = nullptr;
+    uint64_t cap = 0, used = 0;
+    std::vector<uint64_t> offs{0};
+    explicit PinnedBatch(uint64_t bytes) : cap(bytes) {
+        void *p = nullptr;
+        ck(oxg_pinned_alloc(bytes, &p));
+        bases = static_cast<uint8_t *>(p);
+    }
+    ~PinnedBatch() { oxg_pinned_free(bases); }
+    void grow(uint64_t need) {
+        uint64_t ncap = cap;
+        while (ncap < need) ncap *= 2;
+        void *p = nullptr;
+        ck(oxg_pinned_alloc(ncap, &p));
+        memcpy(p, bases, used);
+        oxg_pinned_free(bases);
+        bases = static_cast<uint8_t *>(p);
+        cap = ncap;
+    }
+    void append(const char *d, size_t n) {
+        if (used + n > cap) grow(used + n);
+        memcpy(bases + used, d, n);
+        used += n;
+    }
+    void end_record() { offs.push_back(used); }
+    uint64_t records() const { return offs.size() - 1; }
+    void reset() { used = 0; offs.assign(1, 0); }
+};
+
+py::tuple consume_file(Table &t, const std::string &path, bool skip_bad, uint64_t batch_bytes) {
+    FILE *probe = fopen(path.c_str(), "rb");
+    if (!probe) raise_os_error(path);
+    fclose(probe);
+    gzFile gz = gzopen(path.c_str(), "rb");
+    if (!gz) raise_os_error(path);
+    gzbuffer(gz, 1 << 20);
+    PinnedBatch batch(std::max<uint64_t>(batch_bytes, 1 << 20));
+    uint64_t n_records = 0, n_kmers = 0;
+    auto flush = [&]() {
+        if (batch.records() == 0) return;
+        uint64_t got = 0;
+        try {
+            got = t.consume_csr(batch.bases, batch.offs.data(), batch.records(), skip_bad);
+        } catch (...) { gzclose(gz); throw; }
+        n_kmers += got;
+        n_records += batch.records();
+        batch.reset();
+    };
+    // Line-oriented state machine; gzgets may hand a long line over in several pieces.
+    enum Kind { kNone, kFastaHeader, kFastaSeq, kFastqHeader, kFastqSeq, kFastqPlus, kFastqQual };
+    std::vector<char> piece(1 << 16);
+    int state = 0;  // 0: between records; 1: inside a FASTA record; 2/3/4: FASTQ sequence / '+' / quality line next
+    Kind kind = kNone;
+    bool at_line_start = true, in_record = false;
+    while (gzgets(gz, piece.data(), (int)piece.size())) {
+        size_t n = strlen(piece.data());
+        const bool complete = n && piece[n - 1] == '\n';
+        while (n && (piece[n - 1] == '\n' || piece[n - 1] == '\r')) --n;
+        const char *d = piece.data();
+        if (at_line_start) {
+            if (state <= 1 && n && d[0] == '>') {
+                if (in_record) { batch.end_record(); if (batch.used >= batch_bytes) flush(); }
+                in_record = true;
+                kind = kFastaHeader;
+            } else if (state == 1) kind = kFastaSeq;
+            else if (state == 0 && n && d[0] == '@') { in_record = true; kind = kFastqHeader; }
+            else if (state == 2) kind = kFastqSeq;
+            else if (state == 3) kind = kFastqPlus;
+            else if (state == 4) kind = kFastqQual;
+            else if (n == 0) kind = kNone;  // blank line between records
+            else { gzclose(gz); throw py::value_error("not a FASTA/FASTQ file: " + path); }
+        }
+        if (kind == kFastaSeq || kind == kFastqSeq) batch.append(d, n);
+        if (complete) {
+            switch (kind) {
+            case kFastaHeader: case kFastaSeq: state = 1; break;
+            case kFastqHeader: state = 2; break;
+            case kFastqSeq: state = 3; break;
+            case kFastqPlus: state = 4; break;
+            case kFastqQual:
+                batch.end_record(); in_record = false; state = 0;
+                if (batch.used >= batch_bytes) flush();
+                break;
+            default: break;
+            }
+        }
+        at_line_start = complete;
+    }
+    if (in_record) batch.end_record();  // last FASTA record / truncated FASTQ record
+    flush();
+    gzclose(gz);
+    return py::make_tuple(n_records, n_kmers);
+}
+
 py::set to_pyset(const std::vector<uint64_t> &v) {
     py::set s;
     for (uint64_t x : v) s.add(py::int_(x));
@@ -535,6 +635,10 @@ PYBIND11_MODULE(_oxli, m) {
                  if (op[n_reads] > (uint64_t)b.shape[0]) throw py::value_error("offsets run past the end of bases");
                  return t.consume_csr(static_cast<const uint8_t *>(b.ptr), op, n_reads, skip_bad);
              }, py::arg("bases"), py::arg("offsets"), py::arg("skip_bad_kmers") = true)
+        .def("consume_file", [](Table &t, const std::string &path, bool skip_bad, uint64_t batch_bytes) {
+                 return consume_file(t, path, skip_bad, batch_bytes);
+             }, py::arg("path"), py::arg("skip_bad_kmers") = true, py::arg("batch_bytes") = 256ull << 20,
+             "Count every record of a FASTA/FASTQ file (plain or gzip); returns (records, k-mers counted)")
         .def("union", [](const Table &a, const Table &b) { return to_pyset(a.setop(b, OXG_UNION)); })
         .def("intersection", [](const Table &a, const Table &b) { return to_pyset(a.setop(b, OXG_INTERSECTION)); })
         .def("difference", [](const Table &a, const Table &b) { return to_pyset(a.setop(b, OXG_DIFFERENCE)); })

@@ -281,3 +281,40 @@ def test_consume_many_and_buffer_match_oracle(oxli, example_seq):
     assert a.histo(zero=False) == ora.histo(zero=False) and a.jaccard(b) == 1.0
     with pytest.raises(ValueError, match=r"bad k-mer encountered at position 50 \(read 5\)"):
         oxli.KmerCountTable(21).consume_many(reads, skip_bad_kmers=False)
+
+
+def test_consume_file_fasta_fastq(oxli, tmp_path, example_seq):
+    import gzip as gz
+
+    reads = [example_seq[i:i + 251] for i in range(0, 50000, 173)]
+    reads[3] = reads[3][:100] + "NNN" + reads[3][103:].lower()
+    ora = OracleTable(31)
+    want = sum(ora.consume(r) for r in reads)
+    fq = tmp_path / "r.fq"
+    fq.write_text("".join(f"@r{i} some comment\n{r}\n+\n{'I' * len(r)}\n" for i, r in enumerate(reads)))
+    fa = tmp_path / "r.fa.gz"
+    with gz.open(fa, "wt") as f:  # multi-line FASTA, 60 columns, CRLF on some lines, blank line at the end
+        for i, r in enumerate(reads):
+            f.write(f">r{i}\n")
+            for j in range(0, len(r), 60):
+                f.write(r[j:j + 60] + ("\r\n" if i % 2 else "\n"))
+        f.write("\n")
+    one = tmp_path / "genome.fa"
+    one.write_text(">chr\n" + example_seq[:200000] + "\n")  # one 200-kb line: longer than the read buffer
+    items = [(int(k), int(v)) for k, v in zip(*ora.items_sorted())]
+    for path in (fq, fa):
+        for batch_bytes in (1 << 20, 4096):  # 4 KiB batches: many flushes
+            t = oxli.KmerCountTable(31)
+            assert t.consume_file(str(path), batch_bytes=batch_bytes) == (len(reads), want)
+            assert sorted(t) == items and t.consumed == ora.consumed
+    g, og = oxli.KmerCountTable(21), OracleTable(21)
+    assert g.consume_file(str(one)) == (1, og.consume(example_seq[:200000]))
+    assert sorted(g) == [(int(k), int(v)) for k, v in zip(*og.items_sorted())]
+    with pytest.raises(OSError):
+        g.consume_file(str(tmp_path / "missing.fa"))
+    bad = tmp_path / "bad.txt"
+    bad.write_text("hello\n")
+    with pytest.raises(ValueError, match="not a FASTA/FASTQ file"):
+        g.consume_file(str(bad))
+    with pytest.raises(ValueError, match="bad k-mer encountered at position 70"):
+        oxli.KmerCountTable(31).consume_file(str(fq), skip_bad_kmers=False)
