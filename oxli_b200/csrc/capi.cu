@@ -80,6 +80,7 @@ struct DeviceCtx {
     uint64_t *d_io = nullptr;         uint64_t io_cap = 0;   // generic u64 in/out scratch (device)
     uint64_t *h_io = nullptr;         uint64_t h_io_cap = 0; // pinned mirror
     double *d_f64 = nullptr;          // 4 doubles
+    uint8_t *d_seq = nullptr;         uint64_t seq_cap = 0;  // hash_windows input
 };
 
 std::mutex g_ctx_mu;
@@ -514,27 +515,23 @@ oxg_status oxg_hash_windows(oxg_table *t, const uint8_t *seq, uint64_t len, uint
     if (len < k) return OXG_OK;
     if (!seq || !hashes_out) return fail(OXG_ERR_INVALID, "null argument");
     const uint64_t n_win = len - k + 1;
-    // piecewise so the device-side output stays bounded
+    // piecewise so the device-side output stays bounded; scratch lives in the device context
+    // (hash_kmer / count / get call this once per k-mer)
     const uint64_t piece = 4ull << 20;
-    uint8_t *d_seq = nullptr;
-    uint64_t *d_out = nullptr, *d_off = nullptr;
-    const uint64_t offs[2] = {0, len};
-    CU(cudaMalloc(&d_off, 16));
-    CU(cudaMemcpyAsync(d_off, offs, 16, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMalloc(&d_seq, std::min(len, piece + k - 1) + 16));
-    CU(cudaMalloc(&d_out, std::min(n_win, piece) * 8));
-    oxg_status st = OXG_OK;
-    for (uint64_t lo = 0; lo < n_win && st == OXG_OK; lo += piece) {
+    TRY(ensure_dev(&c->d_seq, &c->seq_cap, std::min(len, piece + k - 1) + 32));
+    TRY(ensure_io(c, std::min(n_win, piece) + 2));
+    uint64_t *d_off = c->d_io + std::min(n_win, piece);
+    c->h_io[0] = 0; c->h_io[1] = len;
+    CU(cudaMemcpyAsync(d_off, c->h_io, 16, cudaMemcpyHostToDevice, c->stream));
+    for (uint64_t lo = 0; lo < n_win; lo += piece) {
         const uint64_t hi = std::min(n_win, lo + piece);
         const uint64_t bytes = hi - lo + k - 1;
-        cudaMemcpyAsync(d_seq, seq + lo, bytes, cudaMemcpyHostToDevice, c->stream);
-        st = run_span(t, kModeHash, d_seq, lo, lo, hi, lo + bytes, d_off, 2, d_out, nullptr);
-        if (st != OXG_OK) break;
-        cudaMemcpyAsync(hashes_out + lo, d_out, (hi - lo) * 8, cudaMemcpyDeviceToHost, c->stream);
-        if (cudaStreamSynchronize(c->stream) != cudaSuccess) st = fail(OXG_ERR_CUDA, "hash_windows: %s", cudaGetErrorString(cudaGetLastError()));
+        CU(cudaMemcpyAsync(c->d_seq, seq + lo, bytes, cudaMemcpyHostToDevice, c->stream));
+        TRY(run_span(t, kModeHash, c->d_seq, lo, lo, hi, lo + bytes, d_off, 2, c->d_io, nullptr));
+        CU(cudaMemcpyAsync(hashes_out + lo, c->d_io, (hi - lo) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
     }
-    cudaFree(d_seq); cudaFree(d_out); cudaFree(d_off);
-    return st;
+    return OXG_OK;
 }
 
 // ---- consume ---------------------------------------------------------------
