@@ -13,6 +13,8 @@
 //   KmerCountTable(ksize, store_kmers=False, *, device=0, capacity_hint=0)
 //   consume_many(seqs, skip_bad_kmers=True)      one GPU batch for many reads
 //   consume_buffer(bases, offsets, skip_bad_kmers=True)   CSR batch, zero-copy from buffers
+//   KmerCountTable(..., deferred=True)           consume(seq) parks reads in a pinned batch and
+//                                                 returns at host speed; see Table::sync
 //   consume_file(path, skip_bad_kmers=True)      FASTA/FASTQ (plain or gzip) parsed into pinned
 //                                                 batches -- the loop the reference leaves to
 //                                                 screed (README.md:89-98)
@@ -103,8 +105,46 @@ struct JsonIn {
     }
 };
 
+// FASTA / FASTQ reader feeding pinned CSR batches to the GPU.  Records are what
+// screed would hand to consume(): FASTA sequence lines joined, FASTQ 4-line records.
+struct PinnedBatch {
+    uint8_t *bases = nullptr;
+    uint64_t cap = 0, used = 0;
+    std::vector<uint64_t> offs{0};
+    explicit PinnedBatch(uint64_t bytes) : cap(bytes) {
+        void *p = nullptr;
+        ck(oxg_pinned_alloc(bytes, &p));
+        bases = static_cast<uint8_t *>(p);
+    }
+    ~PinnedBatch() { oxg_pinned_free(bases); }
+    void grow(uint64_t need) {
+        uint64_t ncap = cap;
+        while (ncap < need) ncap *= 2;
+        void *p = nullptr;
+        ck(oxg_pinned_alloc(ncap, &p));
+        memcpy(p, bases, used);
+        oxg_pinned_free(bases);
+        bases = static_cast<uint8_t *>(p);
+        cap = ncap;
+    }
+    void append(const char *d, size_t n) {
+        if (used + n > cap) grow(used + n);
+        memcpy(bases + used, d, n);
+        used += n;
+    }
+    void end_record() { offs.push_back(used); }
+    uint64_t records() const { return offs.size() - 1; }
+    void reset() { used = 0; offs.assign(1, 0); }
+};
+
 struct Table {
     oxg_table *h = nullptr;
+    // deferred=True: consume(seq) in skip mode only appends the read to a pinned batch and
+    // returns the number of countable windows found by a host scan; the batch goes to the
+    // GPU when it fills up or when any other method needs the table (sync()).
+    bool deferred = false;
+    mutable std::unique_ptr<PinnedBatch> pending;
+    static constexpr uint64_t kPendingBytes = 64ull << 20;
     uint8_t ksize = 0;
     bool store_kmers = false;
     uint64_t consumed = 0;
@@ -112,8 +152,23 @@ struct Table {
     std::unordered_map<uint64_t, std::string> hash_to_kmer;
     int device = 0;
 
-    Table(uint8_t k, bool store, int dev, uint64_t hint) : ksize(k), store_kmers(store), version(oxg_version()), device(dev) {
+    Table(uint8_t k, bool store, int dev, uint64_t hint, bool defer = false)
+        : deferred(defer), ksize(k), store_kmers(store), version(oxg_version()), device(dev) {
         ck(oxg_table_create(dev, k, hint, &h));
+    }
+
+    // push reads parked by deferred consume() calls to the GPU
+    void sync() const {
+        if (!pending || pending->records() == 0) return;
+        uint64_t n = 0, ep = 0;
+        int64_t er = -1;
+        oxg_status st;
+        {
+            py::gil_scoped_release nogil;
+            st = oxg_consume_batch(h, pending->bases, pending->offs.data(), pending->records(), 1, &n, &er, &ep);
+        }
+        pending->reset();
+        ck(st);
     }
     ~Table() { if (h) oxg_table_destroy(h); }
     Table(const Table &) = delete;
@@ -121,6 +176,7 @@ struct Table {
 
     // one hash per window of `seq`; 0 marks a bad window (sourmash force=true)
     std::vector<uint64_t> window_hashes(const std::string &seq) const {
+        sync();
         std::vector<uint64_t> out(seq.size() >= ksize ? seq.size() - ksize + 1 : 0);
         if (!out.empty()) ck(oxg_hash_windows(h, reinterpret_cast<const uint8_t *>(seq.data()), seq.size(), out.data()));
         return out;
@@ -144,6 +200,7 @@ struct Table {
     }
 
     uint64_t count_hash(uint64_t hv) {
+        sync();
         uint64_t now = 0;
         ck(oxg_count_hashes(h, &hv, 1, &now));
         return now;
@@ -160,6 +217,7 @@ struct Table {
     }
 
     uint64_t get_hash(uint64_t hv) const {
+        sync();
         uint64_t c = 0;
         ck(oxg_get_hashes(h, &hv, 1, &c));
         return c;
@@ -172,34 +230,40 @@ struct Table {
     }
 
     std::vector<uint64_t> get_hash_array(const std::vector<uint64_t> &keys) const {
+        sync();
         std::vector<uint64_t> out(keys.size());
         if (!keys.empty()) ck(oxg_get_hashes(h, keys.data(), keys.size(), out.data()));
         return out;
     }
 
     void drop_hash(uint64_t hv) {
+        sync();
         ck(oxg_erase_hashes(h, &hv, 1, nullptr));
     }
 
     uint64_t cut(int mode, uint64_t thresh) {
+        sync();
         uint64_t n = 0;
         ck(oxg_cut(h, mode, thresh, &n));
         return n;
     }
 
     uint64_t len() const {
+        sync();
         uint64_t n = 0;
         ck(oxg_table_len(h, &n));
         return n;
     }
 
     oxg_stats stats() const {
+        sync();
         oxg_stats s{};
         ck(oxg_table_stats(h, &s));
         return s;
     }
 
     std::vector<std::pair<uint64_t, uint64_t>> items(int sort_mode) const {
+        sync();
         uint64_t n = 0;
         ck(oxg_export(h, nullptr, nullptr, 0, sort_mode, &n));
         std::vector<uint64_t> k(n + 1), v(n + 1);
@@ -231,7 +295,21 @@ struct Table {
             }
             if (!good.empty()) ck(oxg_count_hashes(h, good.data(), good.size(), nullptr));
             n = good.size();
+        } else if (deferred && skip_bad) {
+            // host scan: windows without a non-ACGT byte (what the device will count; the
+            // reference's hash==0 skip, probability 2^-64 per k-mer, is not visible here)
+            if (!pending) pending = std::make_unique<PinnedBatch>(kPendingBytes + (1 << 20));
+            int64_t last_bad = -1;
+            for (size_t i = 0; i < seq.size(); ++i) {
+                const char c = seq[i] & ~0x20;
+                if (!is_acgt(c)) last_bad = (int64_t)i;
+                if (i + 1 >= ksize && last_bad < (int64_t)(i + 1 - ksize)) ++n;
+            }
+            pending->append(seq.data(), seq.size());
+            pending->end_record();
+            if (pending->used >= kPendingBytes) sync();
         } else {
+            sync();
             const uint64_t offs[2] = {0, seq.size()};
             int64_t er = -1;
             uint64_t ep = 0;
@@ -246,6 +324,7 @@ struct Table {
     }
 
     uint64_t consume_csr(const uint8_t *bases, const uint64_t *offs, uint64_t n_reads, bool skip_bad) {
+        sync();
         if (store_kmers) throw py::value_error("batch ingest is not available when store_kmers=True");
         uint64_t n = 0, ep = 0;
         int64_t er = -1;
@@ -282,6 +361,7 @@ struct Table {
     }
 
     std::vector<uint64_t> setop(const Table &o, int op) const {
+        sync(); o.sync();
         uint64_t n = 0;
         const uint64_t cap = len() + o.len() + 2;
         std::vector<uint64_t> out(cap);
@@ -315,38 +395,6 @@ struct Table {
         s += '}';
         return s;
     }
-};
-
-// FASTA / FASTQ reader feeding pinned CSR batches to the GPU.  Records are what
-// screed would hand to consume(): FASTA sequence lines joined, FASTQ 4-line records.
-struct PinnedBatch {
-    uint8_t *bases = nullptr;
-    uint64_t cap = 0, used = 0;
-    std::vector<uint64_t> offs{0};
-    explicit PinnedBatch(uint64_t bytes) : cap(bytes) {
-        void *p = nullptr;
-        ck(oxg_pinned_alloc(bytes, &p));
-        bases = static_cast<uint8_t *>(p);
-    }
-    ~PinnedBatch() { oxg_pinned_free(bases); }
-    void grow(uint64_t need) {
-        uint64_t ncap = cap;
-        while (ncap < need) ncap *= 2;
-        void *p = nullptr;
-        ck(oxg_pinned_alloc(ncap, &p));
-        memcpy(p, bases, used);
-        oxg_pinned_free(bases);
-        bases = static_cast<uint8_t *>(p);
-        cap = ncap;
-    }
-    void append(const char *d, size_t n) {
-        if (used + n > cap) grow(used + n);
-        memcpy(bases + used, d, n);
-        used += n;
-    }
-    void end_record() { offs.push_back(used); }
-    uint64_t records() const { return offs.size() - 1; }
-    void reset() { used = 0; offs.assign(1, 0); }
 };
 
 py::tuple consume_file(Table &t, const std::string &path, bool skip_bad, uint64_t batch_bytes) {
@@ -530,11 +578,12 @@ PYBIND11_MODULE(_oxli, m) {
     m.def("device_count", []() { return oxg_device_count(); });
 
     py::class_<Table>(m, "KmerCountTable")
-        .def(py::init([](py::object ksize, bool store_kmers, int device, uint64_t capacity_hint) {
-                 return std::make_unique<Table>(ksize_from_py(ksize), store_kmers, device, capacity_hint);
+        .def(py::init([](py::object ksize, bool store_kmers, int device, uint64_t capacity_hint, bool deferred) {
+                 return std::make_unique<Table>(ksize_from_py(ksize), store_kmers, device, capacity_hint, deferred);
              }),
              py::arg("ksize"), py::arg("store_kmers") = false, py::kw_only(), py::arg("device") = 0,
-             py::arg("capacity_hint") = 0)
+             py::arg("capacity_hint") = 0, py::arg("deferred") = false)
+        .def("flush", &Table::sync, "send reads parked by deferred consume() calls to the GPU")
         .def("hash_kmer", &Table::hash_kmer, py::arg("kmer"))
         .def("unhash", [](const Table &t, uint64_t hv) {
                  if (!t.store_kmers) throw py::value_error("K-mer storage is not enabled.");
@@ -586,6 +635,7 @@ PYBIND11_MODULE(_oxli, m) {
                  return rows;
              }, py::arg("file") = py::none(), py::arg("sortcounts") = false, py::arg("sortkeys") = false)
         .def("histo", [](const Table &t, bool zero) {
+                 t.sync();
                  uint64_t n = 0;
                  ck(oxg_histo(t.h, nullptr, nullptr, 0, &n));
                  std::vector<uint64_t> f(n + 1), c(n + 1);
@@ -655,15 +705,17 @@ PYBIND11_MODULE(_oxli, m) {
         .def("__len__", &Table::len)
         .def("__getitem__", &Table::get)
         .def("__setitem__", [](Table &t, const std::string &kmer, uint64_t count) {
-                 ck(oxg_set_hash(t.h, t.hash_kmer(kmer), count));
+                 const uint64_t hv = t.hash_kmer(kmer);
+                 ck(oxg_set_hash(t.h, hv, count));
              })
         .def("kmers_and_hashes", &Table::kmers_and_hashes, py::arg("seq"), py::arg("skip_bad_kmers") = true)
-        .def("jaccard", [](const Table &a, const Table &b) { double d = 0; ck(oxg_jaccard(a.h, b.h, &d)); return d; })
-        .def("cosine", [](const Table &a, const Table &b) { double d = 0; ck(oxg_cosine(a.h, b.h, &d)); return d; })
+        .def("jaccard", [](const Table &a, const Table &b) { a.sync(); b.sync(); double d = 0; ck(oxg_jaccard(a.h, b.h, &d)); return d; })
+        .def("cosine", [](const Table &a, const Table &b) { a.sync(); b.sync(); double d = 0; ck(oxg_cosine(a.h, b.h, &d)); return d; })
         .def("add", [](Table &a, const Table &b) {  // src/lib.rs:778-837
                  if (a.ksize != b.ksize) throw py::value_error("KmerCountTables must have the same ksize");
                  if (&a == &b) throw std::runtime_error("Already borrowed");
                  uint64_t added = 0, fresh = 0;
+                 a.sync(); b.sync();
                  ck(oxg_merge(a.h, b.h, &added, &fresh));
                  a.consumed += b.consumed;
                  if (a.store_kmers) {
@@ -675,6 +727,6 @@ PYBIND11_MODULE(_oxli, m) {
                  fflush(stdout);
                  return py::make_tuple(added, fresh);
              }, py::arg("other"))
-        .def("reserve", [](Table &t, uint64_t n) { ck(oxg_table_reserve(t.h, n)); }, py::arg("n_keys"))
+        .def("reserve", [](Table &t, uint64_t n) { t.sync(); ck(oxg_table_reserve(t.h, n)); }, py::arg("n_keys"))
         .def_property_readonly("device", [](const Table &t) { return t.device; });
 }

@@ -318,3 +318,22 @@ def test_consume_file_fasta_fastq(oxli, tmp_path, example_seq):
         g.consume_file(str(bad))
     with pytest.raises(ValueError, match="bad k-mer encountered at position 70"):
         oxli.KmerCountTable(31).consume_file(str(fq), skip_bad_kmers=False)
+
+
+def test_deferred_consume_matches_immediate(oxli, example_seq):
+    reads = [example_seq[i:i + 150] for i in range(0, 90000, 61)]
+    reads[7] = "ACGTN" * 30
+    reads[8] = "acgtacgtacgtacgtacgtacgtacgtacgtacgtacgt"
+    reads[9] = "ACG"
+    a, d = oxli.KmerCountTable(21), oxli.KmerCountTable(21, deferred=True)
+    for r in reads:
+        assert d.consume(r) == a.consume(r)
+    assert d.get(reads[0][:21]) == a.get(reads[0][:21])  # any other call flushes the parked reads
+    for r in reads[:50]:
+        assert d.consume(r) == a.consume(r)
+    assert len(d) == len(a) and sorted(d) == sorted(a) and d.consumed == a.consumed
+    assert d.jaccard(a) == 1.0 and d.histo() == a.histo()
+    with pytest.raises(ValueError, match="bad k-mer encountered at position 0"):
+        d.consume("ACGTN" * 30, skip_bad_kmers=False)  # error mode is never deferred
+    d.consume(reads[0]); d.flush()
+    assert d.get(reads[0][:21]) == a.get(reads[0][:21]) + 1
