@@ -303,6 +303,11 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
 #pragma unroll
                 for (int i = 0; i < NX; ++i) { F[i] = f64[i]; R[i] = r64[i]; }
 
+                // Straight-line code for all 8 windows (no branch inside, so the compiler can
+                // interleave the independent murmur chains): the strand is chosen from the
+                // byte-swapped leading word; a tie on those 8 bases (probability 4^-8 on random
+                // sequence) is only recorded here and resolved after the block.
+                uint32_t ties = 0;
                 auto hash_one = [&](auto jc) {
                     constexpr int j = decltype(jc)::value;
                     constexpr int FO = j, RO = Q - K - j;
@@ -314,19 +319,29 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
                     });
                     a[NW - 1] &= TAILMASK;
                     b[NW - 1] &= TAILMASK;
-                    bool use_rc = bswap64(b[0]) < bswap64(a[0]);
-                    if (NW > 1 && a[0] == b[0]) {  // rare: first 8 bases tie
-#pragma unroll
-                        for (int i = 1; i < NW; ++i) {
-                            if (a[i] != b[i]) { use_rc = bswap64(b[i]) < bswap64(a[i]); break; }
-                        }
-                    }
+                    const bool use_rc = bswap64(b[0]) < bswap64(a[0]);
+                    if (NW > 1) ties |= (uint32_t)(a[0] == b[0]) << j;
                     uint64_t w[NW];
 #pragma unroll
                     for (int i = 0; i < NW; ++i) w[i] = use_rc ? b[i] : a[i];
                     h[j] = ((valid >> j) & 1u) ? murmur_words<K>(w) : 0;
                 };
                 static_for<kWPT>(hash_one);
+                ties &= valid;
+                if (NW > 1 && ties) {
+                    // rare: compare the full k-mers byte by byte from shared memory and redo the hash
+                    for (int j = 0; j < kWPT; ++j) {
+                        if (!((ties >> j) & 1u)) continue;
+                        const uint8_t *fw = s_fw + p0 + j, *rc = s_rc + BL - K - p0 - j;
+                        bool use_rc = false;
+                        for (int i = 8; i < K; ++i)
+                            if (fw[i] != rc[i]) { use_rc = rc[i] < fw[i]; break; }
+                        const uint8_t *src = use_rc ? rc : fw;
+                        const uint64_t hv = murmur_bytes([&](int i) -> uint64_t { return src[i]; }, K);
+#pragma unroll
+                        for (int q = 0; q < kWPT; ++q) if (q == j) h[q] = hv;
+                    }
+                }
             }
 
             if (MODE == kModeHash) {
