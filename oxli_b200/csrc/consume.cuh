@@ -113,10 +113,9 @@ __device__ __forceinline__ uint4 load_bases16(const ConsumeParams &p, uint64_t g
 // Stage 16 bytes: forward bytes at s_fw[16v..], mirrored complement at
 // s_rc[BL-16-16v ..], 16 bad bits at s_bad[v].
 template <int BL>
-__device__ __forceinline__ void stage16(const ConsumeParams &p, uint64_t w0, int v, uint8_t *s_fw,
-                                        uint8_t *s_rc, uint16_t *s_bad) {
+__device__ __forceinline__ void stage16_raw(const ConsumeParams &p, uint64_t w0, int v, uint4 raw, uint8_t *s_fw,
+                                            uint8_t *s_rc, uint16_t *s_bad) {
     const uint64_t g = w0 + 16ull * v;
-    uint4 raw = load_bases16(p, g);
     uint32_t u[4] = {upper4(raw.x), upper4(raw.y), upper4(raw.z), upper4(raw.w)};
     uint32_t ok = acgt_mask4(u[0]) | (acgt_mask4(u[1]) << 4) | (acgt_mask4(u[2]) << 8) |
                   (acgt_mask4(u[3]) << 12);
@@ -130,6 +129,24 @@ __device__ __forceinline__ void stage16(const ConsumeParams &p, uint64_t w0, int
                    bswap32(complement4(u[1])), bswap32(complement4(u[0])));
     s_bad[v] = (uint16_t)(~ok);
 }
+
+template <int BL>
+__device__ __forceinline__ void stage16(const ConsumeParams &p, uint64_t w0, int v, uint8_t *s_fw,
+                                        uint8_t *s_rc, uint16_t *s_bad) {
+    stage16_raw<BL>(p, w0, v, load_bases16(p, w0 + 16ull * v), s_fw, s_rc, s_bad);
+}
+
+// ---- cp.async (LDGSTS): global -> shared without passing through registers ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Count up to kWPT hashes per thread (0 = nothing to count).  Fast path: one
 // 256-bit load fetches the key's home bucket (two 16-byte slots = one 32-byte
@@ -215,6 +232,10 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
     __shared__ __align__(16) uint8_t s_rc_all[kWarps][BL];
     __shared__ __align__(8) uint16_t s_bad_all[kWarps][NV + 6 + ((NV + 6) & 1) + 2];
     __shared__ __align__(8) uint32_t s_end_all[kWarps][NE + (NE & 1)];
+    // software pipeline: the next tile's bytes and read boundaries are fetched with cp.async
+    // while the current tile is hashed, so no warp waits on a tile's first loads
+    __shared__ __align__(16) uint8_t s_raw_all[kWarps][2][BL];
+    __shared__ __align__(8) uint64_t s_off_all[kWarps][2][32];
     __shared__ __align__(8) uint64_t s_queue_all[kCounts ? kWarps : 1][kCounts ? kWPT * 32 + kWPT * 4 : 1];  // keys + resume bytes
     __shared__ __align__(8) uint64_t s_route_all[MODE == kModeRoute ? kWarps : 1][MODE == kModeRoute ? 2 * kMaxRanks + 1 + kWarpTile / 8 : 1];
 
@@ -228,6 +249,32 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
     uint64_t n_absorbed = 0;
     bool tiles_left = true;
     bool absorb_left = MODE == kModeRoute && p.n_absorb > 0;
+
+    auto prefetch_raw = [&](uint64_t tile, uint8_t *dst) {
+        if (lane < NV) {
+            const uint64_t g = p.tile_base + tile * kWarpTile + 16ull * lane;
+            const uint32_t n = g >= p.data_end ? 0u : (uint32_t)min((uint64_t)16, p.data_end - g);
+            cp_async16_zfill(dst + 16 * lane, n ? p.bases + (g - p.g0) : p.bases, n);
+        }
+    };
+    auto prefetch_offsets = [&](uint64_t first, uint64_t *dst) {
+        const uint64_t r = first + lane;
+        if (r < p.n_off) cp_async8(dst + lane, p.offsets + r);
+        else dst[lane] = ~0ULL;
+    };
+    auto next_tile_id = [&]() {
+        uint64_t v = 0;
+        if (lane == 0) v = atomicAdd((unsigned long long *)&p.table.ctrl->tile_counter, 1ULL);
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+    uint64_t t_cur = next_tile_id(), t_nxt = next_tile_id();
+    int buf = 0;
+    if (t_cur < p.n_tiles) {
+        prefetch_raw(t_cur, s_raw_all[warp][0]);
+        prefetch_offsets(p.tile_first[t_cur], s_off_all[warp][0]);
+    }
+    cp_async_commit();
+
     while (tiles_left || absorb_left) {
         if (MODE == kModeRoute && absorb_left) {
             // one block of hashes that other ranks routed here (they were stored into this
@@ -255,19 +302,38 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
             }
         }
         if (!tiles_left) continue;
-        uint64_t t = 0;
-        if (lane == 0) t = atomicAdd((unsigned long long *)&p.table.ctrl->tile_counter, 1ULL);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= p.n_tiles) { tiles_left = false; continue; }
+        const uint64_t t = t_cur;
+        if (t >= p.n_tiles) { tiles_left = false; cp_async_wait<0>(); continue; }
         const uint64_t w0 = p.tile_base + t * kWarpTile;
+        uint8_t *s_raw = s_raw_all[warp][buf];
+        const uint64_t *s_off = s_off_all[warp][buf];
 
+        // start on the tile after this one: its id is known already, its bytes go to the
+        // other half of the raw buffer; the id of the tile after that is requested now
+        uint64_t tf_next = 0;
+        if (t_nxt < p.n_tiles) {
+            tf_next = __ldg(p.tile_first + t_nxt);
+            prefetch_raw(t_nxt, s_raw_all[warp][buf ^ 1]);
+        }
+        cp_async_commit();
+        uint64_t t_after = 0;
+        if (lane == 0) t_after = atomicAdd((unsigned long long *)&p.table.ctrl->tile_counter, 1ULL);
+        cp_async_wait<1>();  // everything issued before this iteration (this tile's bytes and boundaries) has landed
         if (lane < NE) s_end[lane] = 0;
         __syncwarp();
-        if (lane < NV) stage16<BL>(p, w0, lane, s_fw, s_rc, s_bad);
-        for (uint64_t r = p.tile_first[t] + lane; r < p.n_off; r += 32) {
-            const uint64_t e = p.offsets[r] - 1 - w0;  // last base of read r-1, tile-relative
-            if (e >= (uint64_t)BL) break;
-            atomicOr(&s_end[e >> 5], 1u << (e & 31));
+
+        if (lane < NV) stage16_raw<BL>(p, w0, lane, *reinterpret_cast<const uint4 *>(s_raw + 16 * lane), s_fw, s_rc, s_bad);
+        {
+            const uint64_t e = s_off[lane] - 1 - w0;  // last base of a read, tile-relative (sentinel: huge)
+            if (e < (uint64_t)BL) atomicOr(&s_end[e >> 5], 1u << (e & 31));
+            if (__shfl_sync(0xffffffffu, e < (uint64_t)BL, 31)) {
+                // more than 32 read boundaries inside one tile (tiny or empty reads): walk the rest
+                for (uint64_t r = p.tile_first[t] + 32 + lane; r < p.n_off; r += 32) {
+                    const uint64_t e2 = p.offsets[r] - 1 - w0;
+                    if (e2 >= (uint64_t)BL) break;
+                    atomicOr(&s_end[e2 >> 5], 1u << (e2 & 31));
+                }
+            }
         }
         bool full = false;
         if (kCounts) full = __ldcg(&p.table.ctrl->size) >= p.table.limit;
@@ -344,6 +410,10 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
                 }
             }
 
+            // the next tile's read boundaries (its tile_first entry has arrived by now)
+            if (t_nxt < p.n_tiles) prefetch_offsets(tf_next, s_off_all[warp][buf ^ 1]);
+            cp_async_commit();
+
             if (MODE == kModeHash) {
 #pragma unroll
                 for (int j = 0; j < kWPT; ++j)
@@ -404,7 +474,14 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
                 if (lane == 0 && tot) atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
             }
         }
+        if (MODE == kModeFirstBad) {
+            if (t_nxt < p.n_tiles) prefetch_offsets(tf_next, s_off_all[warp][buf ^ 1]);
+            cp_async_commit();
+        }
         __syncwarp();  // this warp's shared slice is reused by its next tile
+        t_cur = t_nxt;
+        t_nxt = __shfl_sync(0xffffffffu, t_after, 0);
+        buf ^= 1;
     }
 
     if (MODE == kModeFirstBad) {
