@@ -270,9 +270,16 @@ oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
     };
     switch (k) {
 #define OXG_CASE(KK)                                                                              \
-    case KK:                                                                                      \
-        consume_kernel<KK, MODE><<<grid_of((const void *)consume_kernel<KK, MODE>, 0), kThreads, 0, c->stream>>>(p); \
-        break;
+    case KK: {                                                                                    \
+        const size_t dyn = consume_dyn_smem(MODE);                                                \
+        static bool attr_set = false;                                                             \
+        if (dyn && !attr_set) {                                                                   \
+            CU(cudaFuncSetAttribute(consume_kernel<KK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+            attr_set = true;                                                                      \
+        }                                                                                         \
+        consume_kernel<KK, MODE><<<grid_of((const void *)consume_kernel<KK, MODE>, dyn), kThreads, dyn, c->stream>>>(p); \
+        break;                                                                                    \
+    }
         OXG_CASE(21)
         OXG_CASE(31)
 #undef OXG_CASE

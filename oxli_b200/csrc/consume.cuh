@@ -148,15 +148,29 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Count up to kWPT hashes per thread (0 = nothing to count).  Fast path: one
-// 256-bit load fetches the key's home bucket (two 16-byte slots = one 32-byte
-// sector); a hit in either slot is one RED.  Everything else (displaced keys,
-// new keys, table at its load limit) is compacted into a per-warp shared-memory
-// queue and drained with all lanes busy, so the rare long probe does not leave
-// the warp one-lane-wide.
-__device__ __forceinline__ void count_hashes8(const TableView &tv, const uint64_t (&h)[kWPT], bool full,
-                                              uint64_t *s_queue /* this warp's kWPT*32 entries */,
-                                              uint64_t &n_counted, uint32_t &created) {
+// Count up to kWPT hashes per thread (0 = nothing to count).
+//
+// Fast path: one 256-bit load fetches the key's home bucket (two 16-byte slots = one
+// 32-byte sector); a hit in either slot is one RED.
+//
+// Slow path: keys displaced from their home bucket (16 % at load 0.6), new keys and
+// the "table at its load limit" case go to a per-warp shared-memory queue that
+// persists across tiles.  After every tile ONE probe round runs over the whole queue:
+// each queued key looks at its next bucket; hits and inserts leave the queue, the rest
+// stay with their position advanced.  A key on a long probe chain therefore costs one
+// extra load per tile it rides along, instead of stalling its warp for the whole chain
+// (an ablation of the first version showed the 15 % displaced keys costing 12 of 35 ms:
+// every tile waited for its longest chain, ~6 dependent round trips).
+constexpr int kQueueCap = 512;  // entries per warp; a tile adds at most kWPT*32 = 256
+
+struct SlowQueue {
+    uint64_t *key;   // [kQueueCap]
+    uint8_t *skip;   // [kQueueCap] slots already ruled out, counted from the home slot
+    uint32_t n;      // warp-uniform
+};
+
+__device__ __forceinline__ void count_fast8(const TableView &tv, const uint64_t (&h)[kWPT], SlowQueue &q,
+                                            uint64_t &n_counted) {
     const int lane = threadIdx.x & 31;
     uint32_t pending = 0, restart = 0;
 #pragma unroll
@@ -164,47 +178,71 @@ __device__ __forceinline__ void count_hashes8(const TableView &tv, const uint64_
         uint64_t idx[4];
         ulonglong2 a[4], b[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int j = half * 4 + q;
-            idx[q] = tv.home(h[j]);
-            if (h[j] != 0) load_pair(tv.slots + idx[q], a[q], b[q]);
+        for (int u = 0; u < 4; ++u) {
+            const int j = half * 4 + u;
+            idx[u] = tv.home(h[j]);
+            if (h[j] != 0) load_pair(tv.slots + idx[u], a[u], b[u]);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int j = half * 4 + q;
+        for (int u = 0; u < 4; ++u) {
+            const int j = half * 4 + u;
             if (h[j] == 0) continue;  // bad window, or the reference's hash==0 skip (src/lib.rs:589)
             ++n_counted;
-            if (a[q].x == h[j]) red_add64(&tv.slots[idx[q]].y, 1);
-            else if (b[q].x == h[j]) red_add64(&tv.slots[idx[q] + 1].y, 1);
+            if (a[u].x == h[j]) red_add64(&tv.slots[idx[u]].y, 1);
+            else if (b[u].x == h[j]) red_add64(&tv.slots[idx[u] + 1].y, 1);
             else {
                 pending |= 1u << j;
-                // an empty slot in the home bucket means "maybe insert here": redo that bucket
-                if (a[q].x == kEmpty || b[q].x == kEmpty) restart |= 1u << j;
+                // an empty slot in the home bucket means "maybe insert here": look at it again
+                if (a[u].x == kEmpty || b[u].x == kEmpty) restart |= 1u << j;
             }
         }
     }
-    // queue entry: the key, plus a companion byte telling where to resume probing
-    uint64_t *s_key = s_queue;
-    uint8_t *s_skip = reinterpret_cast<uint8_t *>(s_queue + kWPT * 32);
-    uint32_t qn = 0;  // warp-uniform
 #pragma unroll
     for (int j = 0; j < kWPT; ++j) {
         const bool mine = (pending >> j) & 1u;
         const unsigned m = __ballot_sync(0xffffffffu, mine);
         if (mine) {
-            const uint32_t at = qn + __popc(m & ((1u << lane) - 1));
-            s_key[at] = h[j];
-            s_skip[at] = ((restart >> j) & 1u) ? 0 : 2;
+            const uint32_t at = q.n + __popc(m & ((1u << lane) - 1));
+            q.key[at] = h[j];
+            q.skip[at] = ((restart >> j) & 1u) ? 0 : 2;
         }
-        qn += __popc(m);
+        q.n += __popc(m);
+    }
+}
+
+// One probe round over the queue.  Survivors are compacted to the front (in place: the
+// write cursor never passes the chunk being read, which is held in registers by then).
+__device__ __forceinline__ void slow_round(const TableView &tv, SlowQueue &q, bool full, uint32_t &created) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    uint32_t out = 0;
+    for (uint32_t base = 0; base < q.n; base += 32) {
+        const uint32_t i = base + lane;
+        const bool live = i < q.n;
+        const uint64_t key = live ? q.key[i] : 0;
+        const uint32_t skip = live ? q.skip[i] : 0;
+        __syncwarp();
+        bool again = false;
+        if (live) {
+            const uint64_t idx = (tv.home(key) + skip) & (tv.cap - 1);
+            ulonglong2 a, b;
+            load_pair(tv.slots + idx, a, b);
+            if (key == kEmpty || skip >= 250) created += table_add(tv, key, 1, full);  // out-of-band key / absurd chain
+            else if (a.x == key) red_add64(&tv.slots[idx].y, 1);
+            else if (b.x == key) red_add64(&tv.slots[idx + 1].y, 1);
+            else if (a.x == kEmpty || b.x == kEmpty) created += table_add(tv, key, 1, full);  // claim (or defer when full)
+            else again = true;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, again);
+        if (again) {
+            const uint32_t at = out + __popc(m & ((1u << lane) - 1));
+            q.key[at] = key;
+            q.skip[at] = (uint8_t)(skip + 2);
+        }
+        out += __popc(m);
     }
     __syncwarp();
-    for (uint32_t i = lane; i < qn; i += 32) {
-        const uint64_t key = s_key[i];
-        if (key == kEmpty) { created += table_add(tv, key, 1, full); continue; }
-        created += table_add_buckets(tv, key, 1, full, (tv.home(key) + s_skip[i]) & (tv.cap - 1));
-    }
-    __syncwarp();
+    q.n = out;
 }
 
 // Specialised kernel (k <= 32).  Every warp is an independent worker: it pulls
@@ -236,7 +274,10 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
     // while the current tile is hashed, so no warp waits on a tile's first loads
     __shared__ __align__(16) uint8_t s_raw_all[kWarps][2][BL];
     __shared__ __align__(8) uint64_t s_off_all[kWarps][2][32];
-    __shared__ __align__(8) uint64_t s_queue_all[kCounts ? kWarps : 1][kCounts ? kWPT * 32 + kWPT * 4 : 1];  // keys + resume bytes
+    // dynamic shared memory (see consume_dyn_smem): per warp the slow queue (keys + skip
+    // bytes) and, when routing, the gather buffer for outgoing hashes
+    extern __shared__ __align__(16) uint8_t dyn_smem[];
+    constexpr int kDynPerWarp = kQueueCap * 9 + (MODE == kModeRoute ? kWarpTile * 8 : 0);
     __shared__ __align__(8) uint64_t s_route_all[MODE == kModeRoute ? kWarps : 1][MODE == kModeRoute ? 2 * kMaxRanks + 1 + kWarpTile / 8 : 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -247,6 +288,14 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
     uint64_t first_bad = ~0ULL;
 
     uint64_t n_absorbed = 0;
+    uint8_t *dyn = dyn_smem + (kCounts ? warp * kDynPerWarp : 0);
+    SlowQueue queue{reinterpret_cast<uint64_t *>(dyn), dyn + kQueueCap * 8, 0};
+    uint32_t created = 0;
+    auto flush_created = [&]() {
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
+        if (lane == 0 && tot) atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
+        created = 0;
+    };
     bool tiles_left = true;
     bool absorb_left = MODE == kModeRoute && p.n_absorb > 0;
 
@@ -295,10 +344,10 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
                     h[j] = i < p.absorb_n[seg] ? __ldcs(p.absorb_ptr[seg] + i) : 0;
                 }
                 const bool full = __ldcg(&p.table.ctrl->size) >= p.table.limit;
-                uint32_t created = 0;
-                count_hashes8(p.table, h, full, s_queue_all[warp], n_absorbed, created);
-                const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
-                if (lane == 0 && tot) atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
+                while (queue.n > kQueueCap - kWPT * 32) slow_round(p.table, queue, full, created);
+                count_fast8(p.table, h, queue, n_absorbed);
+                slow_round(p.table, queue, full, created);
+                flush_created();
             }
         }
         if (!tiles_left) continue;
@@ -419,7 +468,6 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
                 for (int j = 0; j < kWPT; ++j)
                     if (gp0 + j >= p.w_lo && gp0 + j < p.w_hi) p.hashes_out[gp0 + j - p.w_lo] = h[j];
             } else if (kCounts) {
-                uint32_t created = 0;
                 if (MODE == kModeRoute) {
                     // Hashes owned by another rank go to that rank's outgoing list -- which may
                     // live in the owner's HBM (peer memory): then these stores ARE the exchange.
@@ -431,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
                     uint32_t *s_rcnt = reinterpret_cast<uint32_t *>(s_route_all[warp]);        // [kMaxRanks]
                     uint32_t *s_rpre = s_rcnt + kMaxRanks;                                     // [kMaxRanks + 1]
                     uint64_t *s_rbase = s_route_all[warp] + kMaxRanks + 1;                     // [kMaxRanks]
-                    uint64_t *s_stage = s_queue_all[warp];                                     // queue is idle now
+                    uint64_t *s_stage = reinterpret_cast<uint64_t *>(dyn + kQueueCap * 9);
                     uint8_t *s_owner = reinterpret_cast<uint8_t *>(s_route_all[warp] + 2 * kMaxRanks + 1);  // [kWarpTile]
                     if (lane < kMaxRanks) s_rcnt[lane] = 0;
                     __syncwarp();
@@ -469,9 +517,10 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
                     }
                     __syncwarp();
                 }
-                count_hashes8(p.table, h, full, s_queue_all[warp], n_counted, created);
-                const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
-                if (lane == 0 && tot) atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
+                while (queue.n > kQueueCap - kWPT * 32) slow_round(p.table, queue, full, created);
+                count_fast8(p.table, h, queue, n_counted);
+                slow_round(p.table, queue, full, created);
+                flush_created();
             }
         }
         if (MODE == kModeFirstBad) {
@@ -484,6 +533,10 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
         buf ^= 1;
     }
 
+    if (kCounts) {
+        while (queue.n) slow_round(p.table, queue, __ldcg(&p.table.ctrl->size) >= p.table.limit, created);
+        flush_created();
+    }
     if (MODE == kModeFirstBad) {
         for (int o = 16; o; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
         if (lane == 0 && first_bad != ~0ULL)
@@ -611,5 +664,13 @@ namespace oxg {
 inline size_t generic_smem_bytes(int k) {
     const int BL = (kTileW + k - 1 + 15) / 16 * 16, NV = BL / 16;
     return (size_t)BL + ((NV * 2 + 15) / 16 * 16) + 16 + (BL / 32 + 3) * 4;
+}
+}  // namespace oxg
+
+namespace oxg {
+// dynamic shared memory a specialised consume launch needs
+inline size_t consume_dyn_smem(int mode) {
+    if (mode != kModeCount && mode != kModeRoute) return 0;
+    return (size_t)(kThreads / 32) * (kQueueCap * 9 + (mode == kModeRoute ? kWarpTile * 8 : 0));
 }
 }  // namespace oxg
