@@ -161,6 +161,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // extra load per tile it rides along, instead of stalling its warp for the whole chain
 // (an ablation of the first version showed the 15 % displaced keys costing 12 of 35 ms:
 // every tile waited for its longest chain, ~6 dependent round trips).
+constexpr int kTileBatch = 8;   // consecutive warp tiles handed out per atomic
 constexpr int kQueueCap = 512;  // entries per warp; a tile adds at most kWPT*32 = 256
 
 struct SlowQueue {
@@ -311,11 +312,22 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
         if (r < p.n_off) cp_async8(dst + lane, p.offsets + r);
         else dst[lane] = ~0ULL;
     };
-    auto next_tile_id = [&]() {
-        uint64_t v = 0;
-        if (lane == 0) v = atomicAdd((unsigned long long *)&p.table.ctrl->tile_counter, 1ULL);
-        return __shfl_sync(0xffffffffu, v, 0);
+    // Tile ids come from one global counter, kTileBatch consecutive tiles per atomic; the
+    // request for the next batch is issued when a batch is opened, so its (serialised, one
+    // hot address for all warps) latency is hidden behind eight tiles of work.
+    uint64_t batch_pos = 0, batch_end = 0, batch_pending = 0;
+    auto request_batch = [&]() {
+        if (lane == 0) batch_pending = atomicAdd((unsigned long long *)&p.table.ctrl->tile_counter, (unsigned long long)kTileBatch);
     };
+    auto next_tile_id = [&]() {
+        if (batch_pos == batch_end) {
+            batch_pos = __shfl_sync(0xffffffffu, batch_pending, 0);
+            batch_end = batch_pos + kTileBatch;
+            request_batch();
+        }
+        return batch_pos++;
+    };
+    request_batch();
     uint64_t t_cur = next_tile_id(), t_nxt = next_tile_id();
     int buf = 0;
     if (t_cur < p.n_tiles) {
@@ -365,8 +377,6 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
             prefetch_raw(t_nxt, s_raw_all[warp][buf ^ 1]);
         }
         cp_async_commit();
-        uint64_t t_after = 0;
-        if (lane == 0) t_after = atomicAdd((unsigned long long *)&p.table.ctrl->tile_counter, 1ULL);
         cp_async_wait<1>();  // everything issued before this iteration (this tile's bytes and boundaries) has landed
         if (lane < NE) s_end[lane] = 0;
         __syncwarp();
@@ -529,7 +539,7 @@ __global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const C
         }
         __syncwarp();  // this warp's shared slice is reused by its next tile
         t_cur = t_nxt;
-        t_nxt = __shfl_sync(0xffffffffu, t_after, 0);
+        t_nxt = next_tile_id();
         buf ^= 1;
     }
 
