@@ -221,6 +221,7 @@ oxg_status zero_ctrl_fields(oxg_table *t, size_t first_field, size_t n_fields) {
 }
 constexpr size_t kFieldCounted = offsetof(Ctrl, counted) / 8;
 constexpr size_t kFieldTile = offsetof(Ctrl, tile_counter) / 8;
+constexpr size_t kLaunchFields = (offsetof(Ctrl, scratch) - offsetof(Ctrl, counted)) / 8;
 constexpr size_t kFieldScratch = offsetof(Ctrl, scratch) / 8;
 
 oxg_status alloc_slots(DeviceCtx *c, uint64_t cap, ulonglong2 **out) {
@@ -318,7 +319,7 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
             if (span <= kSmallBatch) TRY(reserve_keys(t, span));
             else if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
             TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, span));
-            TRY(zero_ctrl_fields(t, kFieldCounted, 5));  // counted, overflow, tile_counter, absorb_*
+            TRY(zero_ctrl_fields(t, kFieldCounted, kLaunchFields));  // counted, overflow, absorbed, tile and absorb counters
         } else {
             TRY(zero_ctrl_fields(t, kFieldTile, 1));
         }
@@ -697,7 +698,7 @@ static oxg_status count_list_device(oxg_table *t, const uint64_t *d_hashes, uint
             if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
             TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, m));
         }
-        TRY(zero_ctrl_fields(t, kFieldCounted, 5));
+        TRY(zero_ctrl_fields(t, kFieldCounted, kLaunchFields));
         CU(cudaEventRecord(c->ev_t0, c->stream));
         count_hashes_kernel<<<grid_for(c, (m + 7) / 8, kOpThreads, 8), kOpThreads, 0, c->stream>>>(view_of(t, optimistic), d_hashes + lo, m, nullptr, skip_zero);
         LAUNCHED();
@@ -1154,7 +1155,7 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
         TRY(ensure_dev(&c->d_tile_first, &c->tile_first_cap, std::max<uint64_t>(n_tiles, 1)));
         if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
         TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, (hi > lo ? hi - lo : 0) + (first ? absorb_total : 0) + 1));
-        TRY(zero_ctrl_fields(t, kFieldCounted, 5));  // counted, overflow, tile_counter, absorb_counter, absorbed
+        TRY(zero_ctrl_fields(t, kFieldCounted, kLaunchFields));
         ConsumeParams p{};
         p.bases = d_bases; p.g0 = 0; p.w_lo = lo; p.w_hi = hi; p.data_end = base_hi;
         p.tile_base = tile_base; p.n_tiles = n_tiles; p.offsets = d_offsets; p.n_off = n_reads + 1;

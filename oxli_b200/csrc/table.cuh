@@ -9,6 +9,7 @@
 // u64 -- including 0 and 2^64-1 -- is a legal key and 0 a legal count.
 // No tombstones: single-key erase shifts the probe run back, bulk cuts rebuild.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -19,17 +20,26 @@ constexpr uint64_t kPhi = 0x9E3779B97F4A7C15ULL;
 constexpr int kMaxProbe = 1024;
 
 struct Ctrl {              // lives in device memory, mirrored to pinned host memory
+    // line 0: table state, read by every warp (size) -- kept apart from the hot atomics
     uint64_t size;         // live keys in slots[]
     uint64_t side_present; // key kEmpty is present
     uint64_t side_count;   // its count
+    uint64_t first_bad;    // error-mode scan: smallest bad window start
+    uint64_t pad0[12];
+    // line 1: per-launch counters (zeroed together before every consume launch)
     uint64_t counted;      // k-mers counted by the running consume launch
     uint64_t overflow;     // entries appended to the overflow list
-    uint64_t tile_counter; // dynamic tile scheduler of the running consume launch
-    uint64_t absorb_counter; // same, for blocks of received hashes (sharded route launches)
     uint64_t absorbed;     // received hashes counted by the running launch
-    uint64_t first_bad;    // error-mode scan: smallest bad window start
-    uint64_t scratch[10];  // per-op outputs (stats, set sizes, ...)
+    uint64_t pad1[13];
+    // lines 2 and 3: the two work counters every warp hits with atomics
+    uint64_t tile_counter;   // dynamic tile scheduler of the running consume launch
+    uint64_t pad2[15];
+    uint64_t absorb_counter; // same, for blocks of received hashes (sharded route launches)
+    uint64_t pad3[15];
+    uint64_t scratch[16];  // per-op outputs (stats, set sizes, ...)
 };
+static_assert(offsetof(Ctrl, counted) == 128 && offsetof(Ctrl, tile_counter) == 256 &&
+              offsetof(Ctrl, absorb_counter) == 384 && offsetof(Ctrl, scratch) == 512, "Ctrl layout");
 
 struct TableView {
     ulonglong2 *slots;
