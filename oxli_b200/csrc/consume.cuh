@@ -162,7 +162,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // (an ablation of the first version showed the 15 % displaced keys costing 12 of 35 ms:
 // every tile waited for its longest chain, ~6 dependent round trips).
 constexpr int kTileBatch = 8;   // consecutive warp tiles handed out per atomic
-constexpr int kQueueCap = 512;  // entries per warp; a tile adds at most kWPT*32 = 256
+constexpr int kQueueCap = 320;  // entries per warp; a tile adds at most kWPT*32 = 256
 
 struct SlowQueue {
     uint64_t *key;   // [kQueueCap]
