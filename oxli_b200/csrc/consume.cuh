@@ -252,7 +252,7 @@ __device__ __forceinline__ void slow_round(const TableView &tv, SlowQueue &q, bo
 // first version used 2048-window CTA tiles; ncu showed 30 % of all stall samples
 // at the CTA barrier waiting for the one warp stuck in a long probe.)
 template <int K, int MODE>
-__global__ void __launch_bounds__(kThreads, OXG_MIN_CTAS) consume_kernel(const ConsumeParams p) {
+__global__ void __launch_bounds__(kThreads, MODE == kModeRoute ? 2 : OXG_MIN_CTAS) consume_kernel(const ConsumeParams p) {
     static_assert(K >= 1 && K <= 32, "specialised kernel covers k <= 32");
     constexpr int Q = 8 * ((K + 7 + 7) / 8);  // bytes a thread pulls per strand
     constexpr int BL = ((kWarpTile - 8 + Q) + 15) / 16 * 16;
