@@ -112,6 +112,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic_per_launch(kmers_per_launch: float):
+    """dram__bytes_read+write of the consume kernel from the committed ncu capture,
+    scaled to this run's k-mers per launch (same workload shape); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)
+        return t["dram_bytes_per_launch"] * kmers_per_launch / t["kmers_per_launch"]
+    except Exception:
+        return None
+
+
 def alg_bytes_per_kmer(read_len: int, k: int) -> float:
     # SURVEY.md 8(d): every base read once (1 B) + 16-B slot read + 8-B count write
     return read_len / (read_len - k + 1) + 24.0
@@ -226,7 +237,10 @@ def main():
     kmers_per_launch = kmers_per_step * a.steps / max(kernel_launches, 1)
     achieved = balg * kmers_per_launch / (avg_launch_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": f"consume_kernel<{k},count>", "alg_bytes_per_kmer": balg,
+                "traffic": measured_traffic_per_launch(kmers_per_launch) if (k, L) == (31, 150) else None,
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json)",
+                "alg_bytes_per_launch": balg * kmers_per_launch,
+                "kernel": f"consume_kernel<{k},count>", "alg_bytes_per_kmer": balg,
                 "kmers_per_launch": kmers_per_launch, "avg_launch_ms": avg_launch_ms,
                 "kernel_share_of_step": kernel_ms / dev_ms, "peak_source": peak_src}
 
