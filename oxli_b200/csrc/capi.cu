@@ -181,9 +181,8 @@ uint64_t capacity_for_keys(uint64_t keys) {
 struct oxg_table {
     DeviceCtx *ctx = nullptr;
     uint32_t k = 0;
-    Slots slots{nullptr, nullptr, nullptr};  // one allocation: keys | hi | lo
+    ulonglong2 *slots = nullptr;
     uint64_t cap = 0;
-    uint64_t red_headroom = 0;  // +1s the RED path may still add to any one slot before lo could wrap
     Ctrl *d_ctrl = nullptr;
     Ctrl *h_ctrl = nullptr;  // pinned
     uint64_t size = 0;       // host mirror of ctrl->size as of the last sync
@@ -195,7 +194,7 @@ namespace {
 
 TableView view_of(const oxg_table *t, bool with_overflow) {
     TableView v;
-    v.s = t->slots;
+    v.slots = t->slots;
     v.cap = t->cap;
     uint32_t lg = 0;
     while ((1ull << lg) < t->cap) ++lg;
@@ -225,31 +224,11 @@ constexpr size_t kFieldTile = offsetof(Ctrl, tile_counter) / 8;
 constexpr size_t kLaunchFields = (offsetof(Ctrl, scratch) - offsetof(Ctrl, counted)) / 8;
 constexpr size_t kFieldScratch = offsetof(Ctrl, scratch) / 8;
 
-oxg_status alloc_slots(DeviceCtx *c, uint64_t cap, Slots *out) {
-    void *p = nullptr;
-    CU(cudaMalloc(&p, cap * 20));  // 8 (keys) + 8 (hi) + 4 (lo) bytes per slot
-    out->keys = static_cast<uint64_t *>(p);
-    out->hi = out->keys + cap;
-    out->lo = reinterpret_cast<uint32_t *>(out->hi + cap);
+oxg_status alloc_slots(DeviceCtx *c, uint64_t cap, ulonglong2 **out) {
+    CU(cudaMalloc(out, cap * sizeof(ulonglong2)));
     init_slots_kernel<<<grid_for(c, cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(*out, cap);
     LAUNCHED();
     CU(cudaGetLastError());
-    return OXG_OK;
-}
-
-constexpr uint64_t kRedHeadroom = 1ull << 31;  // lo < 2^31 after normalisation, must stay < 2^32
-
-// Make sure a launch may add `adds` ones to a single slot through the RED path.
-oxg_status ensure_red_headroom(oxg_table *t, uint64_t adds) {
-    DeviceCtx *c = t->ctx;
-    if (adds >= kRedHeadroom) return fail(OXG_ERR_INVALID, "internal: launch too large for the 32-bit count path");
-    if (t->red_headroom < adds) {
-        normalize_kernel<<<grid_for(c, t->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(t->slots, t->cap);
-        LAUNCHED();
-        CU(cudaGetLastError());
-        t->red_headroom = kRedHeadroom;
-    }
-    t->red_headroom -= adds;
     return OXG_OK;
 }
 
@@ -258,9 +237,9 @@ oxg_status grow_to_fit(oxg_table *t, uint64_t keys) {
     uint64_t want = std::max(capacity_for_keys(keys), pow2_at_least(keys * 2));
     if (want <= t->cap) return OXG_OK;
     DeviceCtx *c = t->ctx;
-    Slots fresh{};
+    ulonglong2 *fresh = nullptr;
     TRY(alloc_slots(c, want, &fresh));
-    const Slots old = t->slots;
+    ulonglong2 *old = t->slots;
     const uint64_t old_cap = t->cap;
     t->slots = fresh;
     t->cap = want;
@@ -270,7 +249,7 @@ oxg_status grow_to_fit(oxg_table *t, uint64_t keys) {
         CU(cudaGetLastError());
     }
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaFree(old.keys));
+    CU(cudaFree(old));
     return OXG_OK;
 }
 
@@ -340,7 +319,6 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
             if (span <= kSmallBatch) TRY(reserve_keys(t, span));
             else if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
             TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, span));
-            TRY(ensure_red_headroom(t, span));
             TRY(zero_ctrl_fields(t, kFieldCounted, kLaunchFields));  // counted, overflow, absorbed, tile and absorb counters
         } else {
             TRY(zero_ctrl_fields(t, kFieldTile, 1));
@@ -368,7 +346,6 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
             if (ov) {  // table hit its load limit: grow, then replay the deferred hashes
                 if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
                 TRY(grow_to_fit(t, t->size + ov));
-                TRY(ensure_red_headroom(t, ov));
                 count_hashes_kernel<<<grid_for(c, ov, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr, 0);
                 LAUNCHED();
                 CU(cudaGetLastError());
@@ -459,7 +436,6 @@ oxg_status oxg_table_create(int device, uint32_t ksize, uint64_t capacity_hint, 
     CU(cudaMallocHost(&t->h_ctrl, sizeof(Ctrl)));
     memset(t->h_ctrl, 0, sizeof(Ctrl));
     TRY(alloc_slots(c, t->cap, &t->slots));
-    t->red_headroom = kRedHeadroom;
     CU(cudaStreamSynchronize(c->stream));
     *out = t.release();
     return OXG_OK;
@@ -470,7 +446,7 @@ oxg_status oxg_table_destroy(oxg_table *t) {
     std::lock_guard<std::mutex> lk(t->ctx->mu);
     cudaSetDevice(t->ctx->dev);
     cudaStreamSynchronize(t->ctx->stream);
-    cudaFree(t->slots.keys);
+    cudaFree(t->slots);
     cudaFree(t->d_ctrl);
     cudaFreeHost(t->h_ctrl);
     delete t;
@@ -490,7 +466,6 @@ oxg_status oxg_table_clear(oxg_table *t) {
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(t->d_ctrl, 0, sizeof(Ctrl), c->stream));
     t->size = 0;
-    t->red_headroom = kRedHeadroom;
     return OXG_OK;
 }
 
@@ -723,7 +698,6 @@ static oxg_status count_list_device(oxg_table *t, const uint64_t *d_hashes, uint
             if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
             TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, m));
         }
-        TRY(ensure_red_headroom(t, m));
         TRY(zero_ctrl_fields(t, kFieldCounted, kLaunchFields));
         CU(cudaEventRecord(c->ev_t0, c->stream));
         count_hashes_kernel<<<grid_for(c, (m + 7) / 8, kOpThreads, 8), kOpThreads, 0, c->stream>>>(view_of(t, optimistic), d_hashes + lo, m, nullptr, skip_zero);
@@ -739,7 +713,6 @@ static oxg_status count_list_device(oxg_table *t, const uint64_t *d_hashes, uint
         if (ov) {
             if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
             TRY(grow_to_fit(t, t->size + ov));
-            TRY(ensure_red_headroom(t, ov));
             count_hashes_kernel<<<grid_for(c, (ov + 7) / 8, kOpThreads, 8), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr, 0);
             LAUNCHED();
             CU(cudaGetLastError());
@@ -766,9 +739,6 @@ oxg_status oxg_count_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, ui
     TRY(ensure_io(c, 2 * n));
     memcpy(c->h_io, hashes, n * 8);
     CU(cudaMemcpyAsync(c->d_io, c->h_io, n * 8, cudaMemcpyHostToDevice, c->stream));
-    if (n >= kRedHeadroom) return fail(OXG_ERR_INVALID, "pass at most 2^31-1 hashes per call");
-    if (new_counts) t->red_headroom = 0;  // exact path: lo may end up anywhere below 2^32
-    else TRY(ensure_red_headroom(t, n));
     count_hashes_kernel<<<grid_for(c, n, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_io, n, new_counts ? c->d_io + n : nullptr, 0);
     LAUNCHED();
     CU(cudaGetLastError());
@@ -787,7 +757,6 @@ oxg_status oxg_add_pairs(oxg_table *t, const uint64_t *keys, const uint64_t *val
     memcpy(c->h_io, keys, n * 8);
     memcpy(c->h_io + n, vals, n * 8);
     CU(cudaMemcpyAsync(c->d_io, c->h_io, 2 * n * 8, cudaMemcpyHostToDevice, c->stream));
-    t->red_headroom = 0;  // exact path: lo may end up anywhere below 2^32
     add_pairs_kernel<<<grid_for(c, n, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_io, c->d_io + n, n);
     LAUNCHED();
     CU(cudaGetLastError());
@@ -843,16 +812,16 @@ oxg_status oxg_cut(oxg_table *t, int mode, uint64_t thresh, uint64_t *n_removed)
     if (mode != 0 && mode != 1) return fail(OXG_ERR_INVALID, "mode must be 0 (mincut) or 1 (maxcut)");
     TRY(pull_ctrl(t));
     uint64_t removed = 0;
-    Slots fresh{};
+    ulonglong2 *fresh = nullptr;
     TRY(alloc_slots(c, t->cap, &fresh));
-    const Slots old = t->slots;
+    ulonglong2 *old = t->slots;
     t->slots = fresh;
     TRY(zero_ctrl_fields(t, kFieldScratch, 1));
     cut_kernel<<<grid_for(c, t->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(old, t->cap, view_of(t, false), mode, thresh);
     LAUNCHED();
     CU(cudaGetLastError());
     TRY(pull_ctrl(t));
-    CU(cudaFree(old.keys));
+    CU(cudaFree(old));
     removed = t->h_ctrl->scratch[0];
     t->h_ctrl->size -= removed;
     if (t->h_ctrl->side_present) {
@@ -1104,7 +1073,7 @@ oxg_status oxg_cosine(oxg_table *a, oxg_table *b, double *out) {
     cosine_kernel<<<grid_for(c, a->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(a, false), view_of(b, false), c->d_f64);
     LAUNCHED();
     TableView none = view_of(a, false);
-    none.s.keys = nullptr;  // norm-only pass over b: adds nothing to any dot product
+    none.slots = nullptr;  // norm-only pass over b: adds nothing to any dot product
     cosine_kernel<<<grid_for(c, b->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(b, false), none, c->d_f64 + 1);
     LAUNCHED();
     CU(cudaGetLastError());
@@ -1131,7 +1100,6 @@ oxg_status oxg_merge(oxg_table *dst, oxg_table *src, uint64_t *counts_added, uin
     TRY(pull_ctrl(src));
     TRY(reserve_keys(dst, src->h_ctrl->size));
     TRY(zero_ctrl_fields(dst, kFieldScratch, 2));
-    dst->red_headroom = 0;  // exact path: lo may end up anywhere below 2^32
     merge_kernel<<<grid_for(c, src->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(dst, false), view_of(src, false));
     LAUNCHED();
     CU(cudaGetLastError());
@@ -1187,7 +1155,6 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
         TRY(ensure_dev(&c->d_tile_first, &c->tile_first_cap, std::max<uint64_t>(n_tiles, 1)));
         if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
         TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, (hi > lo ? hi - lo : 0) + (first ? absorb_total : 0) + 1));
-        TRY(ensure_red_headroom(t, (hi > lo ? hi - lo : 0) + (first ? absorb_total : 0)));
         TRY(zero_ctrl_fields(t, kFieldCounted, kLaunchFields));
         ConsumeParams p{};
         p.bases = d_bases; p.g0 = 0; p.w_lo = lo; p.w_hi = hi; p.data_end = base_hi;
@@ -1226,7 +1193,6 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
         if (ov) {
             if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
             TRY(grow_to_fit(t, t->size + ov));
-            TRY(ensure_red_headroom(t, ov));
             count_hashes_kernel<<<grid_for(c, (ov + 7) / 8, kOpThreads, 8), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr, 0);
             LAUNCHED();
             CU(cudaGetLastError());

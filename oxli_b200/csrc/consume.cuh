@@ -150,10 +150,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // Count up to kWPT hashes per thread (0 = nothing to count).
 //
-// Fast path: one 256-bit load fetches the four keys of the home bucket (one 32-byte
-// sector of the key array); a hit is one RED.ADD.U32 on the count's low word.
+// Fast path: one 256-bit load fetches the key's home bucket (two 16-byte slots = one
+// 32-byte sector); a hit in either slot is one RED.
 //
-// Slow path: keys displaced from their home bucket (6.5 % at load 0.6), new keys and
+// Slow path: keys displaced from their home bucket (16 % at load 0.6), new keys and
 // the "table at its load limit" case go to a per-warp shared-memory queue that
 // persists across tiles.  After every tile ONE probe round runs over the whole queue:
 // each queued key looks at its next bucket; hits and inserts leave the queue, the rest
@@ -176,27 +176,25 @@ __device__ __forceinline__ void count_fast8(const TableView &tv, const uint64_t 
     uint32_t pending = 0, restart = 0;
 #pragma unroll
     for (int half = 0; half < kWPT / 4; ++half) {
-        uint64_t idx[4], k[4][kBucket];
+        uint64_t idx[4];
+        ulonglong2 a[4], b[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = half * 4 + u;
             idx[u] = tv.home(h[j]);
-            if (h[j] != 0) load_keys4(tv.s.keys + idx[u], k[u]);
+            if (h[j] != 0) load_pair(tv.slots + idx[u], a[u], b[u]);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = half * 4 + u;
             if (h[j] == 0) continue;  // bad window, or the reference's hash==0 skip (src/lib.rs:589)
             ++n_counted;
-            int hit = -1;
-            bool empty = false;
-#pragma unroll
-            for (int s = 0; s < kBucket; ++s) { if (k[u][s] == h[j]) hit = s; empty |= k[u][s] == kEmpty; }
-            if (hit >= 0) count_red1(tv, idx[u] + hit);
+            if (a[u].x == h[j]) red_add64(&tv.slots[idx[u]].y, 1);
+            else if (b[u].x == h[j]) red_add64(&tv.slots[idx[u] + 1].y, 1);
             else {
                 pending |= 1u << j;
                 // an empty slot in the home bucket means "maybe insert here": look at it again
-                if (empty) restart |= 1u << j;
+                if (a[u].x == kEmpty || b[u].x == kEmpty) restart |= 1u << j;
             }
         }
     }
@@ -207,7 +205,7 @@ __device__ __forceinline__ void count_fast8(const TableView &tv, const uint64_t 
         if (mine) {
             const uint32_t at = q.n + __popc(m & ((1u << lane) - 1));
             q.key[at] = h[j];
-            q.skip[at] = ((restart >> j) & 1u) ? 0 : kBucket;
+            q.skip[at] = ((restart >> j) & 1u) ? 0 : 2;
         }
         q.n += __popc(m);
     }
@@ -228,25 +226,19 @@ __device__ __forceinline__ void slow_round(const TableView &tv, SlowQueue &q, bo
         bool again = false;
         if (live) {
             const uint64_t idx = (tv.home(key) + skip) & (tv.cap - 1);
-            if (key == kEmpty || skip >= 248) {
-                created += table_inc1_from(tv, key, full, tv.home(key));  // out-of-band key / absurd chain
-            } else {
-                uint64_t k[kBucket];
-                load_keys4(tv.s.keys + idx, k);
-                int hit = -1;
-                bool empty = false;
-#pragma unroll
-                for (int s = 0; s < kBucket; ++s) { if (k[s] == key) hit = s; empty |= k[s] == kEmpty; }
-                if (hit >= 0) count_red1(tv, idx + hit);
-                else if (empty) created += table_inc1_from(tv, key, full, idx);  // claim (or defer when full)
-                else again = true;
-            }
+            ulonglong2 a, b;
+            load_pair(tv.slots + idx, a, b);
+            if (key == kEmpty || skip >= 250) created += table_add(tv, key, 1, full);  // out-of-band key / absurd chain
+            else if (a.x == key) red_add64(&tv.slots[idx].y, 1);
+            else if (b.x == key) red_add64(&tv.slots[idx + 1].y, 1);
+            else if (a.x == kEmpty || b.x == kEmpty) created += table_add(tv, key, 1, full);  // claim (or defer when full)
+            else again = true;
         }
         const unsigned m = __ballot_sync(0xffffffffu, again);
         if (again) {
             const uint32_t at = out + __popc(m & ((1u << lane) - 1));
             q.key[at] = key;
-            q.skip[at] = (uint8_t)(skip + kBucket);
+            q.skip[at] = (uint8_t)(skip + 2);
         }
         out += __popc(m);
     }

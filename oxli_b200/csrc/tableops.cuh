@@ -20,23 +20,14 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
 }
 
 // HashMap::new / clear
-__global__ void init_slots_kernel(Slots s, uint64_t cap) {
-    for (uint64_t i = gtid(); i < cap; i += gstride()) { s.keys[i] = kEmpty; s.lo[i] = 0; s.hi[i] = 0; }
+__global__ void init_slots_kernel(ulonglong2 *slots, uint64_t cap) {
+    for (uint64_t i = gtid(); i < cap; i += gstride()) slots[i] = make_ulonglong2(kEmpty, 0);
 }
 
-// Restores the headroom of the RED path: afterwards every lo is below 2^31 (table.cuh).
-__global__ void normalize_kernel(Slots s, uint64_t cap) {
-    for (uint64_t i = gtid(); i < cap; i += gstride()) {
-        const uint32_t l = s.lo[i];
-        if (l >> 31) { s.lo[i] = l & 0x7fffffffu; s.hi[i] += 0x80000000ull; }
-    }
-}
-
-// count_hash for a list (src/lib.rs:100-104); room was reserved by the host (or the view
-// carries a deferral list).  Without new_counts: 4 keys per thread per round, all home
-// buckets (one 256-bit load of four keys each) requested before the first is examined, +1
-// through the RED path; zero keys are skipped when skip_zero is set (hash streams mark
-// uncountable windows with 0).
+// count_hash for a list (src/lib.rs:100-104); room was reserved by the host.
+// Without new_counts: 8 keys per thread per round, all home buckets (one 256-bit
+// load each) requested before the first is examined; zero keys are skipped when
+// skip_zero is set (the hash stream of the two-kernel pipeline marks bad windows 0).
 __global__ void __launch_bounds__(kOpThreads) count_hashes_kernel(TableView t, const uint64_t *__restrict__ hashes, uint64_t n,
                                     uint64_t *__restrict__ new_counts, int skip_zero) {
     uint32_t created = 0;
@@ -45,12 +36,13 @@ __global__ void __launch_bounds__(kOpThreads) count_hashes_kernel(TableView t, c
         for (uint64_t i = gtid(); i < n; i += gstride())
             new_counts[i] = table_add_fetch(t, hashes[i], 1, &created);
     } else {
-        constexpr int U = 4;
+        constexpr int U = 8;
         const uint64_t stride = gstride();
         for (uint64_t base = gtid(); base < n; base += stride * U) {
             // at the load limit new keys are deferred to the overflow list (if there is one)
             const bool full = t.overflow != nullptr && __ldcg(&t.ctrl->size) >= t.limit;
-            uint64_t h[U], idx[U], k[U][kBucket];
+            uint64_t h[U], idx[U];
+            ulonglong2 a[U], b[U];
             bool live[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -58,22 +50,22 @@ __global__ void __launch_bounds__(kOpThreads) count_hashes_kernel(TableView t, c
                 live[u] = i < n;
                 h[u] = live[u] ? __ldcs(hashes + i) : 0;
                 if (skip_zero && h[u] == 0) live[u] = false;
-                if (h[u] == kEmpty) { if (live[u]) { created += table_inc1_from(t, h[u], full, 0); ++counted; } live[u] = false; }
+                if (h[u] == kEmpty) { if (live[u]) { created += table_add(t, h[u], 1, full); ++counted; } live[u] = false; }
                 idx[u] = t.home(h[u]);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (live[u]) load_keys4(t.s.keys + idx[u], k[u]);
+                if (live[u]) load_pair(t.slots + idx[u], a[u], b[u]);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (!live[u]) continue;
                 ++counted;
-                int hit = -1;
-                bool empty = false;
-#pragma unroll
-                for (int q = 0; q < kBucket; ++q) { if (k[u][q] == h[u]) hit = q; empty |= k[u][q] == kEmpty; }
-                if (hit >= 0) count_red1(t, idx[u] + hit);
-                else created += table_inc1_from(t, h[u], full, empty ? idx[u] : ((idx[u] + kBucket) & (t.cap - 1)));
+                if (a[u].x == h[u]) red_add64(&t.slots[idx[u]].y, 1);
+                else if (b[u].x == h[u]) red_add64(&t.slots[idx[u] + 1].y, 1);
+                else {
+                    const bool redo = a[u].x == kEmpty || b[u].x == kEmpty;
+                    created += table_add_buckets(t, h[u], 1, full, (idx[u] + (redo ? 0 : 2)) & (t.cap - 1));
+                }
             }
         }
     }
@@ -105,9 +97,9 @@ __global__ void set_hash_kernel(TableView t, uint64_t key, uint64_t value) {
     if (key == kEmpty) { t.ctrl->side_present = 1; t.ctrl->side_count = value; return; }
     uint64_t i = t.home(key);
     for (;;) {
-        const uint64_t k = t.s.keys[i];
-        if (k == key) { count_store(t, i, value); return; }
-        if (k == kEmpty) { t.s.keys[i] = key; count_store(t, i, value); t.ctrl->size += 1; return; }
+        ulonglong2 s = t.slots[i];
+        if (s.x == key) { t.slots[i].y = value; return; }
+        if (s.x == kEmpty) { t.slots[i] = make_ulonglong2(key, value); t.ctrl->size += 1; return; }
         i = (i + 1) & (t.cap - 1);
     }
 }
@@ -127,16 +119,16 @@ __global__ void erase_hashes_kernel(TableView t, const uint64_t *__restrict__ ha
         int64_t f = table_find(t, key);
         if (f < 0) continue;
         uint64_t hole = (uint64_t)f, j = hole;
-        t.s.keys[hole] = kEmpty; t.s.lo[hole] = 0; t.s.hi[hole] = 0;
+        t.slots[hole] = make_ulonglong2(kEmpty, 0);
         for (;;) {
             j = (j + 1) & mask;
-            const uint64_t k = t.s.keys[j];
-            if (k == kEmpty) break;
-            const uint64_t hm = t.home(k);
-            // the entry at j may move into the hole iff its home is not cyclically inside (hole, j]
+            ulonglong2 s = t.slots[j];
+            if (s.x == kEmpty) break;
+            const uint64_t hm = t.home(s.x);
+            // s may move into the hole iff its home is not cyclically inside (hole, j]
             if (((j - hm) & mask) >= ((j - hole) & mask)) {
-                t.s.keys[hole] = k; t.s.lo[hole] = t.s.lo[j]; t.s.hi[hole] = t.s.hi[j];
-                t.s.keys[j] = kEmpty; t.s.lo[j] = 0; t.s.hi[j] = 0;
+                t.slots[hole] = s;
+                t.slots[j] = make_ulonglong2(kEmpty, 0);
                 hole = j;
             }
         }
@@ -146,32 +138,24 @@ __global__ void erase_hashes_kernel(TableView t, const uint64_t *__restrict__ ha
     t.ctrl->scratch[0] = removed;
 }
 
-// growth: re-insert every live entry of the old arrays (keys are unique: plain stores)
-__global__ void rehash_kernel(Slots old, uint64_t old_cap, TableView nt) {
-    uint32_t created = 0;
+// growth: re-insert every live entry of the old slot array
+__global__ void rehash_kernel(const ulonglong2 *__restrict__ old_slots, uint64_t old_cap, TableView nt) {
     for (uint64_t i = gtid(); i < old_cap; i += gstride()) {
-        const uint64_t k = old.keys[i];
-        if (k == kEmpty) continue;
-        const uint64_t slot = table_slot_for(nt, k, false, nt.home(k), &created);
-        nt.s.lo[slot] = old.lo[i];
-        nt.s.hi[slot] = old.hi[i];
+        ulonglong2 s = old_slots[i];
+        if (s.x != kEmpty) table_add(nt, s.x, s.y, false);
     }
 }
 
 // mincut / maxcut (src/lib.rs:227-267): rebuild keeping the survivors.
 // mode 0 drops count < thresh, mode 1 drops count > thresh.
-__global__ void cut_kernel(Slots old, uint64_t old_cap, TableView nt, int mode, uint64_t thresh) {
+__global__ void cut_kernel(const ulonglong2 *__restrict__ old_slots, uint64_t old_cap, TableView nt,
+                           int mode, uint64_t thresh) {
     uint64_t removed = 0;
-    uint32_t created = 0;
     for (uint64_t i = gtid(); i < old_cap; i += gstride()) {
-        const uint64_t k = old.keys[i];
-        if (k == kEmpty) continue;
-        const uint64_t v = old.hi[i] + old.lo[i];
-        const bool drop = mode == 0 ? (v < thresh) : (v > thresh);
-        if (drop) { ++removed; continue; }
-        const uint64_t slot = table_slot_for(nt, k, false, nt.home(k), &created);
-        nt.s.lo[slot] = old.lo[i];
-        nt.s.hi[slot] = old.hi[i];
+        ulonglong2 s = old_slots[i];
+        if (s.x == kEmpty) continue;
+        const bool drop = mode == 0 ? (s.y < thresh) : (s.y > thresh);
+        if (drop) ++removed; else table_add(nt, s.x, s.y, false);
     }
     removed = warp_sum(removed);
     if ((threadIdx.x & 31) == 0 && removed) atomicAdd((unsigned long long *)&nt.ctrl->scratch[0], (unsigned long long)removed);
@@ -186,8 +170,9 @@ __global__ void stats_kernel(TableView t, uint64_t *__restrict__ dense, uint64_t
     __syncthreads();
     uint64_t len = 0, sum = 0, mn = ~0ULL, mx = 0;
     for (uint64_t i = gtid(); i < t.cap; i += gstride()) {
-        if (t.s.keys[i] == kEmpty) continue;
-        const uint64_t v = t.s.hi[i] + t.s.lo[i];
+        ulonglong2 s = t.slots[i];
+        if (s.x == kEmpty) continue;
+        const uint64_t v = s.y;
         ++len; sum += v; mn = min(mn, v); mx = max(mx, v);
         if (dense) {
             if (v < kHistSmem) atomicAdd(&bins[v], 1u);
@@ -217,14 +202,15 @@ __global__ void stats_kernel(TableView t, uint64_t *__restrict__ dense, uint64_t
 
 // ---- ordered export: hashes / dump / __iter__ (src/lib.rs:330-381, 517-521, 658-662)
 // pass 1: live slots per chunk of kExportChunk slots
-__global__ void export_count_kernel(Slots s, uint64_t cap, uint64_t *__restrict__ chunk_counts) {
+__global__ void export_count_kernel(const ulonglong2 *__restrict__ slots, uint64_t cap,
+                                    uint64_t *__restrict__ chunk_counts) {
     __shared__ uint32_t total;
     if (threadIdx.x == 0) total = 0;
     __syncthreads();
     const uint64_t base = blockIdx.x * (uint64_t)kExportChunk;
     uint32_t c = 0;
     for (uint32_t i = threadIdx.x; i < kExportChunk; i += blockDim.x)
-        if (base + i < cap && s.keys[base + i] != kEmpty) ++c;
+        if (base + i < cap && slots[base + i].x != kEmpty) ++c;
     c = (uint32_t)warp_sum(c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&total, c);
     __syncthreads();
@@ -251,18 +237,19 @@ __global__ void export_scan_kernel(uint64_t *__restrict__ chunk_counts, uint64_t
 }
 
 // pass 2: write (key,count) of live slots in slot order
-__global__ void export_write_kernel(Slots s, uint64_t cap, const uint64_t *__restrict__ chunk_offsets,
+__global__ void export_write_kernel(const ulonglong2 *__restrict__ slots, uint64_t cap,
+                                    const uint64_t *__restrict__ chunk_offsets,
                                     uint64_t *__restrict__ keys, uint64_t *__restrict__ vals,
                                     uint64_t out_cap) {
     constexpr int PER = kExportChunk / kOpThreads;  // consecutive slots per thread
     __shared__ uint32_t pre[kOpThreads];
     const uint64_t base = blockIdx.x * (uint64_t)kExportChunk + threadIdx.x * (uint64_t)PER;
-    uint64_t k[PER];
+    ulonglong2 s[PER];
     uint32_t c = 0;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-        k[i] = base + i < cap ? s.keys[base + i] : kEmpty;
-        c += k[i] != kEmpty;
+        s[i] = base + i < cap ? slots[base + i] : make_ulonglong2(kEmpty, 0);
+        c += s[i].x != kEmpty;
     }
     pre[threadIdx.x] = c;
     __syncthreads();
@@ -274,8 +261,8 @@ __global__ void export_write_kernel(Slots s, uint64_t cap, const uint64_t *__res
     uint64_t at = chunk_offsets[blockIdx.x] + pre[threadIdx.x];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-        if (k[i] == kEmpty) continue;
-        if (at < out_cap) { keys[at] = k[i]; if (vals) vals[at] = s.hi[base + i] + s.lo[base + i]; }
+        if (s[i].x == kEmpty) continue;
+        if (at < out_cap) { keys[at] = s[i].x; if (vals) vals[at] = s[i].y; }
         ++at;
     }
 }
@@ -284,7 +271,7 @@ __global__ void export_write_kernel(Slots s, uint64_t cap, const uint64_t *__res
 __global__ void setop_count_kernel(TableView a, TableView b) {
     uint64_t both = 0;
     for (uint64_t i = gtid(); i < a.cap; i += gstride()) {
-        const uint64_t k = a.s.keys[i];
+        const uint64_t k = a.slots[i].x;
         if (k != kEmpty && table_find(b, k) >= 0) ++both;
     }
     both = warp_sum(both);
@@ -296,7 +283,7 @@ __global__ void setop_export_kernel(TableView a, TableView b, int want_in_b, uin
                                     uint64_t out_cap, uint64_t *out_count) {
     const uint64_t n = (a.cap + 31) / 32 * 32;  // keep warps whole for the ballots
     for (uint64_t i = gtid(); i < n; i += gstride()) {
-        const uint64_t k = i < a.cap ? a.s.keys[i] : kEmpty;
+        const uint64_t k = i < a.cap ? a.slots[i].x : kEmpty;
         bool emit = k != kEmpty;
         if (emit && want_in_b != 2) emit = (table_find(b, k) >= 0) == (want_in_b == 1);
         const unsigned m = __ballot_sync(0xffffffffu, emit);
@@ -311,16 +298,15 @@ __global__ void setop_export_kernel(TableView a, TableView b, int want_in_b, uin
 }
 
 // cosine (src/lib.rs:727-765): scratch[0] = sum_{k in A&B} a_k*b_k (wrapping u64),
-// sumsq_a += sum a_k^2 as doubles; b.s.keys == nullptr: norm only
+// scratch_f64[0] += sum a_k^2 as doubles
 __global__ void cosine_kernel(TableView a, TableView b, double *__restrict__ sumsq_a) {
     uint64_t dot = 0;
     double sq = 0.0;
     for (uint64_t i = gtid(); i < a.cap; i += gstride()) {
-        const uint64_t k = a.s.keys[i];
-        if (k == kEmpty) continue;
-        const uint64_t v = a.s.hi[i] + a.s.lo[i];
-        sq += (double)v * (double)v;
-        if (b.s.keys) dot += v * table_get(b, k);
+        ulonglong2 s = a.slots[i];
+        if (s.x == kEmpty) continue;
+        sq += (double)s.y * (double)s.y;
+        if (b.slots) dot += s.y * table_get(b, s.x);
     }
     dot = warp_sum(dot);
     for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
@@ -336,12 +322,11 @@ __global__ void merge_kernel(TableView dst, TableView src) {
     uint64_t added = 0, fresh = 0;
     uint32_t created = 0;
     for (uint64_t i = gtid(); i < src.cap; i += gstride()) {
-        const uint64_t k = src.s.keys[i];
-        if (k == kEmpty) continue;
-        const uint64_t v = src.s.hi[i] + src.s.lo[i];
-        const uint64_t after = table_add_fetch(dst, k, v, &created);
-        if (after - v == 0) ++fresh;
-        added += v;
+        ulonglong2 s = src.slots[i];
+        if (s.x == kEmpty) continue;
+        const uint64_t after = table_add_fetch(dst, s.x, s.y, &created);
+        if (after - s.y == 0) ++fresh;
+        added += s.y;
     }
     added = warp_sum(added); fresh = warp_sum(fresh);
     const uint64_t cr = warp_sum(created);
