@@ -25,7 +25,7 @@ __global__ void init_slots_kernel(ulonglong2 *slots, uint64_t cap) {
 }
 
 // count_hash for a list (src/lib.rs:100-104); room was reserved by the host.
-// Without new_counts: 8 keys per thread per round, all home buckets (one 256-bit
+// Without new_counts: 4 keys per thread per round (8 was slower: scripts/microbench_probe.cu), all home buckets (one 256-bit
 // load each) requested before the first is examined; zero keys are skipped when
 // skip_zero is set (the hash stream of the two-kernel pipeline marks bad windows 0).
 __global__ void __launch_bounds__(kOpThreads) count_hashes_kernel(TableView t, const uint64_t *__restrict__ hashes, uint64_t n,
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kOpThreads) count_hashes_kernel(TableView t, c
         for (uint64_t i = gtid(); i < n; i += gstride())
             new_counts[i] = table_add_fetch(t, hashes[i], 1, &created);
     } else {
-        constexpr int U = 8;
+        constexpr int U = 4;
         const uint64_t stride = gstride();
         for (uint64_t base = gtid(); base < n; base += stride * U) {
             // at the load limit new keys are deferred to the overflow list (if there is one)
