@@ -9,6 +9,7 @@
 #include <cstddef>
 #include <future>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -53,7 +54,7 @@ oxg_status fail(oxg_status st, const char *fmt, ...) {
     } while (0)
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
-constexpr uint64_t kChunkBytes = 64ull << 20;     // host->device streaming granule
+static const uint64_t kChunkBytes = [] { const char *e = getenv("OXLI_B200_CHUNK_MB"); return (e ? (uint64_t)atoi(e) : 64ull) << 20; }();  // host->device streaming granule
 constexpr uint64_t kLaunchWindows = 64ull << 20;  // windows per consume launch (bounds the overflow list)
 constexpr uint64_t kSmallBatch = 1ull << 20;      // below this, reserve for the worst case up front
 constexpr uint64_t kMinCap = 1024;
@@ -619,11 +620,10 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
         // run_span blocks on the stream after every launch, so the next chunk's staging
         // (host memcpy into pinned memory + H2D on the copy stream) runs on a helper
         // thread and overlaps this chunk's kernels
+        // (also for pinned sources: slicing the offsets is host work that should not delay the launch)
         std::future<oxg_status> next;
-        if (ci + 1 < n_chunks) {
-            if (src_pinned) TRY(issue_copy(ci + 1));
-            else next = std::async(std::launch::async, [&, ci] { cudaSetDevice(c->dev); return issue_copy(ci + 1); });
-        }
+        if (ci + 1 < n_chunks)
+            next = std::async(std::launch::async, [&, ci] { cudaSetDevice(c->dev); return issue_copy(ci + 1); });
         oxg_status st = run_span(t, mode, c->d_stage[b], lo, std::max(lo, w_lo), std::min(w_hi, lo + kChunkBytes), hi,
                                  c->d_offs[b], n_off, nullptr, counted);
         if (next.valid()) {
