@@ -187,6 +187,8 @@ struct oxg_table {
     Ctrl *d_ctrl = nullptr;
     Ctrl *h_ctrl = nullptr;  // pinned
     uint64_t size = 0;       // host mirror of ctrl->size as of the last sync
+    bool hinted = false;     // the caller said how many distinct keys to expect
+    uint64_t last_new = 0;   // keys created by the previous consume launch (growth look-ahead)
     float last_ms = 0.f;
     uint64_t last_launches = 0;
 };
@@ -226,7 +228,7 @@ constexpr size_t kLaunchFields = (offsetof(Ctrl, scratch) - offsetof(Ctrl, count
 constexpr size_t kFieldScratch = offsetof(Ctrl, scratch) / 8;
 
 oxg_status alloc_slots(DeviceCtx *c, uint64_t cap, ulonglong2 **out) {
-    CU(cudaMalloc(out, cap * sizeof(ulonglong2)));
+    CU(cudaMalloc(out, cap * sizeof(ulonglong2)));  // (cudaMallocAsync pools were 2x slower for growing multi-GB tables)
     init_slots_kernel<<<grid_for(c, cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(*out, cap);
     LAUNCHED();
     CU(cudaGetLastError());
@@ -318,7 +320,16 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
         if (mode == kModeCount) {
             const uint64_t span = hi - lo;
             if (span <= kSmallBatch) TRY(reserve_keys(t, span));
-            else if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
+            else {
+                // Look ahead instead of running into the load limit mid-launch: a table nobody
+                // sized gets at least one slot per 8 windows of a full launch (128 MiB for 64 Mi
+                // windows: enough for high-coverage data, cheap if it is not), and if the
+                // previous launch created keys at a rate that would cross the limit, grow now.
+                if (!t->hinted && t->cap < pow2_at_least(span / 8)) TRY(grow_to_fit(t, span / 16));
+                const uint64_t expect = t->size + t->last_new + t->last_new / 4;
+                if (expect * 10 > t->cap * 7) TRY(grow_to_fit(t, expect));
+                else if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
+            }
             TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, span));
             TRY(zero_ctrl_fields(t, kFieldCounted, kLaunchFields));  // counted, overflow, absorbed, tile and absorb counters
         } else {
@@ -338,12 +349,14 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
         else TRY(launch_consume<kModeFirstBad>(t, p));
         CU(cudaEventRecord(c->ev_t1, c->stream));
         if (mode == kModeCount) {
+            const uint64_t size_before = t->size;
             TRY(pull_ctrl(t));
             float ms = 0.f;
             CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
             t->last_ms += ms; t->last_launches += 1;
             if (counted) *counted += t->h_ctrl->counted;
             uint64_t ov = t->h_ctrl->overflow;
+            t->last_new = (hi - lo) > kSmallBatch ? (t->size - size_before) + ov : 0;
             if (ov) {  // table hit its load limit: grow, then replay the deferred hashes
                 if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
                 TRY(grow_to_fit(t, t->size + ov));
@@ -432,6 +445,7 @@ oxg_status oxg_table_create(int device, uint32_t ksize, uint64_t capacity_hint, 
     auto t = std::make_unique<oxg_table>();
     t->ctx = c; t->k = ksize;
     t->cap = capacity_for_keys(capacity_hint);
+    t->hinted = capacity_hint != 0;
     CU(cudaMalloc(&t->d_ctrl, sizeof(Ctrl)));
     CU(cudaMemsetAsync(t->d_ctrl, 0, sizeof(Ctrl), c->stream));
     CU(cudaMallocHost(&t->h_ctrl, sizeof(Ctrl)));

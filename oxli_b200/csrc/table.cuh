@@ -68,8 +68,16 @@ __device__ __forceinline__ void load_pair(const ulonglong2 *p, ulonglong2 &a, ul
         : "l"(p));
 }
 
+// Deferred hashes go to one list with one cursor: the lanes that arrive together reserve
+// their entries with a single atomic (a launch that fills the table defers tens of
+// millions of hashes; one atomic each on one address cost 7x the kernel time).
 __device__ __forceinline__ void push_overflow(const TableView &t, uint64_t key) {
-    uint64_t at = atomicAdd((unsigned long long *)&t.ctrl->overflow, 1ULL);
+    const unsigned peers = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd((unsigned long long *)&t.ctrl->overflow, (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const uint64_t at = base + __popc(peers & ((1u << lane) - 1));
     if (t.overflow && at < t.overflow_cap) t.overflow[at] = key;
 }
 
