@@ -366,6 +366,10 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeRoute ? 2 : OXG_MIN_CTA
         const uint64_t t = t_cur;
         if (t >= p.n_tiles) { tiles_left = false; cp_async_wait<0>(); continue; }
         const uint64_t w0 = p.tile_base + t * kWarpTile;
+        if (MODE == kModeFirstBad && w0 > __ldcg(&p.table.ctrl->first_bad)) {
+            // a bad window before this tile is already known: nothing later can be the first
+            tiles_left = false; cp_async_wait<0>(); continue;
+        }
         uint8_t *s_raw = s_raw_all[warp][buf];
         const uint64_t *s_off = s_off_all[warp][buf];
 
