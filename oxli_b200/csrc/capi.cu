@@ -356,7 +356,11 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
             t->last_ms += ms; t->last_launches += 1;
             if (counted) *counted += t->h_ctrl->counted;
             uint64_t ov = t->h_ctrl->overflow;
-            t->last_new = (hi - lo) > kSmallBatch ? (t->size - size_before) + ov : 0;
+            // what the next launch of this stream will probably create: the rate of the last
+            // quarter of this one (high-coverage input finds its keys early and then stops
+            // creating them; the whole-launch count would quadruple the table for nothing),
+            // or everything it wanted when it ran into the limit
+            t->last_new = (hi - lo) <= kSmallBatch ? 0 : ov ? (t->size - size_before) + ov : 4 * t->h_ctrl->late_new;
             if (ov) {  // table hit its load limit: grow, then replay the deferred hashes
                 if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
                 TRY(grow_to_fit(t, t->size + ov));

@@ -292,9 +292,13 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeRoute ? 2 : OXG_MIN_CTA
     uint8_t *dyn = dyn_smem + (kCounts ? warp * kDynPerWarp : 0);
     SlowQueue queue{reinterpret_cast<uint64_t *>(dyn), dyn + kQueueCap * 8, 0};
     uint32_t created = 0;
+    bool late = false;  // working on the last quarter of the launch's tiles
     auto flush_created = [&]() {
         const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
-        if (lane == 0 && tot) atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
+        if (lane == 0 && tot) {
+            atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
+            if (late) atomicAdd((unsigned long long *)&p.table.ctrl->late_new, (unsigned long long)tot);
+        }
         created = 0;
     };
     bool tiles_left = true;
@@ -366,6 +370,7 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeRoute ? 2 : OXG_MIN_CTA
         const uint64_t t = t_cur;
         if (t >= p.n_tiles) { tiles_left = false; cp_async_wait<0>(); continue; }
         const uint64_t w0 = p.tile_base + t * kWarpTile;
+        late = t * 4 >= p.n_tiles * 3;
         if (MODE == kModeFirstBad && w0 > __ldcg(&p.table.ctrl->first_bad)) {
             // a bad window before this tile is already known: nothing later can be the first
             tiles_left = false; cp_async_wait<0>(); continue;
@@ -657,7 +662,10 @@ __global__ void __launch_bounds__(kThreads) consume_generic_kernel(const Consume
         }
         if (MODE == kModeCount) {
             const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
-            if ((tid & 31) == 0 && tot) atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
+            if ((tid & 31) == 0 && tot) {
+                atomicAdd((unsigned long long *)&p.table.ctrl->size, (unsigned long long)tot);
+                if (t * 4 >= p.n_tiles * 3) atomicAdd((unsigned long long *)&p.table.ctrl->late_new, (unsigned long long)tot);
+            }
         }
         __syncthreads();
     }

@@ -30,7 +30,8 @@ struct Ctrl {              // lives in device memory, mirrored to pinned host me
     uint64_t counted;      // k-mers counted by the running consume launch
     uint64_t overflow;     // entries appended to the overflow list
     uint64_t absorbed;     // received hashes counted by the running launch
-    uint64_t pad1[13];
+    uint64_t late_new;     // keys created by the last quarter of the launch's tiles (growth look-ahead)
+    uint64_t pad1[12];
     // lines 2 and 3: the two work counters every warp hits with atomics
     uint64_t tile_counter;   // dynamic tile scheduler of the running consume launch
     uint64_t pad2[15];
