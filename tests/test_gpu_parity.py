@@ -204,6 +204,29 @@ def test_growth_from_tiny_table(capi):
     assert_same_table(t, ora)
 
 
+def test_high_coverage_input_does_not_inflate_the_table(capi):
+    """Several launches over reads that keep re-covering one small genome: every key is created by
+    the first launch, and the growth look-ahead must not enlarge a table that already fits them
+    (a 4x larger table costs a third of the throughput on BASELINE.json configs[1])."""
+    k, L, n, G = 31, 150, 1_400_000, 500_000   # 210 Mbases = 4 launches of 64 Mi windows
+    d_bases = capi.device_alloc(n * L + 64)
+    d_offs = capi.device_alloc((n + 1) * 8)
+    try:
+        capi.synth_reads_device(d_bases, n, L, G, seed=11)
+        capi.h2d(d_offs, uniform_offsets(n, L))
+        for hint in (G, 0):
+            t = capi.Table(k, capacity_hint=hint)
+            st, total, _, _ = t.consume_batch_device(d_bases, d_offs, n, n * L, True)
+            assert st == 0 and total == n * (L - k + 1)
+            assert G - k <= len(t) <= G
+            assert t.capacity * 16 <= 128 << 20, t.capacity
+            if hint:
+                assert t.capacity == capi.Table(k, capacity_hint=hint).capacity
+    finally:
+        capi.device_free(d_bases)
+        capi.device_free(d_offs)
+
+
 def test_multi_chunk_streaming(capi):
     # > 2 host chunks (64 MiB each) from pageable memory; reads straddle chunk edges
     k, L, n, G = 31, 151, 900_000, 300_000
