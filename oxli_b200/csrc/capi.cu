@@ -67,6 +67,7 @@ struct DeviceCtx {
     // double-buffered staging for host batches
     uint8_t *d_stage[2] = {nullptr, nullptr};
     uint8_t *h_stage[2] = {nullptr, nullptr};
+    uint64_t d_stage_cap[2] = {0, 0}, h_stage_cap[2] = {0, 0};
     uint64_t *d_offs[2] = {nullptr, nullptr};
     uint64_t *h_offs[2] = {nullptr, nullptr};
     uint64_t offs_cap[2] = {0, 0};
@@ -594,10 +595,24 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
     const uint64_t base0 = offsets[0];
     const uint64_t first = w_lo & ~(uint64_t)(kTileW - 1);
     const uint64_t n_chunks = (w_hi - first + kChunkBytes - 1) / kChunkBytes;
-    const uint64_t stage_bytes = kChunkBytes + 256 + 16;
-    for (int b = 0; b < 2; ++b) {
-        if (!c->d_stage[b]) CU(cudaMalloc(&c->d_stage[b], stage_bytes));
-        if (!src_pinned && !c->h_stage[b]) CU(cudaMallocHost(&c->h_stage[b], stage_bytes));
+    // staging sized to the batch (pinning 2 x 64 MiB costs a third of a second; a caller
+    // that hands over a few thousand reads should not pay it), full chunks once one is needed
+    const uint64_t stage_bytes = std::min(pow2_at_least(std::max<uint64_t>(data_end - first, 1 << 20)), kChunkBytes) + 256 + 16;
+    for (int b = 0; b < (n_chunks > 1 ? 2 : 1); ++b) {
+        if (c->d_stage_cap[b] < stage_bytes) {
+            CU(cudaStreamSynchronize(c->stream));
+            if (c->d_stage[b]) CU(cudaFree(c->d_stage[b]));
+            c->d_stage[b] = nullptr; c->d_stage_cap[b] = 0;
+            CU(cudaMalloc(&c->d_stage[b], stage_bytes));
+            c->d_stage_cap[b] = stage_bytes;
+        }
+        if (!src_pinned && c->h_stage_cap[b] < stage_bytes) {
+            CU(cudaStreamSynchronize(c->copy));
+            if (c->h_stage[b]) CU(cudaFreeHost(c->h_stage[b]));
+            c->h_stage[b] = nullptr; c->h_stage_cap[b] = 0;
+            CU(cudaMallocHost(&c->h_stage[b], stage_bytes));
+            c->h_stage_cap[b] = stage_bytes;
+        }
     }
     auto issue_copy = [&](uint64_t ci) -> oxg_status {
         const int b = (int)(ci & 1);

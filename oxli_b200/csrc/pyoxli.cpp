@@ -298,7 +298,7 @@ struct Table {
         } else if (deferred && skip_bad) {
             // host scan: windows without a non-ACGT byte (what the device will count; the
             // reference's hash==0 skip, probability 2^-64 per k-mer, is not visible here)
-            if (!pending) pending = std::make_unique<PinnedBatch>(kPendingBytes + (1 << 20));
+            if (!pending) pending = std::make_unique<PinnedBatch>(1 << 20);  // doubles as reads arrive, flushed at kPendingBytes
             int64_t last_bad = -1;
             for (size_t i = 0; i < seq.size(); ++i) {
                 const char c = seq[i] & ~0x20;
@@ -404,7 +404,7 @@ py::tuple consume_file(Table &t, const std::string &path, bool skip_bad, uint64_
     gzFile gz = gzopen(path.c_str(), "rb");
     if (!gz) raise_os_error(path);
     gzbuffer(gz, 1 << 20);
-    PinnedBatch batch(std::max<uint64_t>(batch_bytes, 1 << 20));
+    PinnedBatch batch(4 << 20);  // grows by doubling towards batch_bytes: a small file should not pin 256 MiB
     uint64_t n_records = 0, n_kmers = 0;
     auto flush = [&]() {
         if (batch.records() == 0) return;

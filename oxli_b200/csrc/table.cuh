@@ -193,4 +193,42 @@ __device__ __forceinline__ uint64_t table_get(const TableView &t, uint64_t key) 
     return i < 0 ? 0 : __ldcg(&t.slots[i].y);
 }
 
+// U lookups per thread with all home-bucket loads in flight together (one dependent random
+// sector each is what bounds get / set comparison; a thread that waits for one at a time
+// leaves the memory system idle).  cnt[j] = count or 0; returns the found mask.
+template <int U>
+__device__ __forceinline__ uint32_t table_get_many(const TableView &t, const uint64_t (&key)[U], uint32_t live,
+                                                   uint64_t (&cnt)[U]) {
+    ulonglong2 s0[U], s1[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        cnt[j] = 0;
+        // dead and out-of-band keys load bucket 0: harmless, keeps the loads unconditional
+        const uint64_t h = ((live >> j) & 1) && key[j] != kEmpty ? t.home(key[j]) : 0;
+        load_pair(t.slots + h, s0[j], s1[j]);
+    }
+    uint32_t found = 0;
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+        if (!((live >> j) & 1)) continue;
+        const uint64_t k = key[j];
+        if (k == kEmpty) {
+            if (t.ctrl->side_present) { cnt[j] = t.ctrl->side_count; found |= 1u << j; }
+        } else if (s0[j].x == k) { cnt[j] = s0[j].y; found |= 1u << j; }
+        else if (s0[j].x == kEmpty) {}
+        else if (s1[j].x == k) { cnt[j] = s1[j].y; found |= 1u << j; }
+        else if (s1[j].x == kEmpty) {}
+        else {  // displaced past its home bucket: walk on
+            uint64_t i = (t.home(k) + 2) & (t.cap - 1);
+            for (uint64_t probe = 2; probe < t.cap; ++probe) {
+                const ulonglong2 s = load_slot(t.slots + i);
+                if (s.x == k) { cnt[j] = s.y; found |= 1u << j; break; }
+                if (s.x == kEmpty) break;
+                i = (i + 1) & (t.cap - 1);
+            }
+        }
+    }
+    return found;
+}
+
 }  // namespace oxg

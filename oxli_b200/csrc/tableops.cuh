@@ -88,7 +88,22 @@ __global__ void add_pairs_kernel(TableView t, const uint64_t *__restrict__ keys,
 // get_hash / get_hash_array (src/lib.rs:185-194)
 __global__ void get_hashes_kernel(TableView t, const uint64_t *__restrict__ hashes, uint64_t n,
                                   uint64_t *__restrict__ out) {
-    for (uint64_t i = gtid(); i < n; i += gstride()) out[i] = table_get(t, hashes[i]);
+    constexpr int U = 4;
+    const uint64_t stride = gstride();
+    for (uint64_t base = gtid(); base < n; base += stride * U) {
+        uint64_t key[U], cnt[U];
+        uint32_t live = 0;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const uint64_t i = base + j * stride;
+            key[j] = i < n ? hashes[i] : 0;
+            live |= (i < n ? 1u : 0u) << j;
+        }
+        table_get_many<U>(t, key, live, cnt);
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+            if ((live >> j) & 1) out[base + j * stride] = cnt[j];
+    }
 }
 
 // __setitem__: counts.insert(hash, value) (src/lib.rs:675-681).  One thread.
@@ -269,10 +284,19 @@ __global__ void export_write_kernel(const ulonglong2 *__restrict__ slots, uint64
 
 // ---- set comparisons (src/lib.rs:610-638, 708-722): |A & B| by probing B with A's keys
 __global__ void setop_count_kernel(TableView a, TableView b) {
+    constexpr int U = 4;
     uint64_t both = 0;
-    for (uint64_t i = gtid(); i < a.cap; i += gstride()) {
-        const uint64_t k = a.slots[i].x;
-        if (k != kEmpty && table_find(b, k) >= 0) ++both;
+    const uint64_t stride = gstride();
+    for (uint64_t base = gtid(); base < a.cap; base += stride * U) {
+        uint64_t key[U], cnt[U];
+        uint32_t live = 0;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const uint64_t i = base + j * stride;
+            key[j] = i < a.cap ? __ldcs(&a.slots[i].x) : kEmpty;
+            live |= (key[j] != kEmpty ? 1u : 0u) << j;
+        }
+        if (live) both += __popc(table_get_many<U>(b, key, live, cnt));
     }
     both = warp_sum(both);
     if ((threadIdx.x & 31) == 0 && both) atomicAdd((unsigned long long *)&a.ctrl->scratch[0], (unsigned long long)both);
@@ -302,11 +326,27 @@ __global__ void setop_export_kernel(TableView a, TableView b, int want_in_b, uin
 __global__ void cosine_kernel(TableView a, TableView b, double *__restrict__ sumsq_a) {
     uint64_t dot = 0;
     double sq = 0.0;
-    for (uint64_t i = gtid(); i < a.cap; i += gstride()) {
-        ulonglong2 s = a.slots[i];
-        if (s.x == kEmpty) continue;
-        sq += (double)s.y * (double)s.y;
-        if (b.slots) dot += s.y * table_get(b, s.x);
+    constexpr int U = 4;
+    const uint64_t stride = gstride();
+    for (uint64_t base = gtid(); base < a.cap; base += stride * U) {
+        uint64_t key[U], mine[U], cnt[U];
+        uint32_t live = 0;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const uint64_t i = base + j * stride;
+            const ulonglong2 s = i < a.cap ? a.slots[i] : make_ulonglong2(kEmpty, 0);
+            key[j] = s.x; mine[j] = s.y;
+            live |= (s.x != kEmpty ? 1u : 0u) << j;
+        }
+        if (!live) continue;
+#pragma unroll
+        for (int j = 0; j < U; ++j)
+            if ((live >> j) & 1) sq += (double)mine[j] * (double)mine[j];
+        if (b.slots) {
+            table_get_many<U>(b, key, live, cnt);
+#pragma unroll
+            for (int j = 0; j < U; ++j) dot += mine[j] * cnt[j];
+        }
     }
     dot = warp_sum(dot);
     for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
