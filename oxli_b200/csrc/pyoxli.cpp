@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cerrno>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -160,14 +161,18 @@ struct Table {
     // push reads parked by deferred consume() calls to the GPU
     void sync() const {
         if (!pending || pending->records() == 0) return;
+        // the batch leaves `pending` before the GIL is released: a consume() from another
+        // Python thread meanwhile starts a fresh one instead of appending to memory in flight
+        std::unique_ptr<PinnedBatch> batch = std::move(pending);
         uint64_t n = 0, ep = 0;
         int64_t er = -1;
         oxg_status st;
         {
             py::gil_scoped_release nogil;
-            st = oxg_consume_batch(h, pending->bases, pending->offs.data(), pending->records(), 1, &n, &er, &ep);
+            st = oxg_consume_batch(h, batch->bases, batch->offs.data(), batch->records(), 1, &n, &er, &ep);
         }
-        pending->reset();
+        batch->reset();
+        if (!pending) pending = std::move(batch);
         ck(st);
     }
     ~Table() { if (h) oxg_table_destroy(h); }
@@ -578,11 +583,18 @@ PYBIND11_MODULE(_oxli, m) {
     m.def("device_count", []() { return oxg_device_count(); });
 
     py::class_<Table>(m, "KmerCountTable")
-        .def(py::init([](py::object ksize, bool store_kmers, int device, uint64_t capacity_hint, bool deferred) {
-                 return std::make_unique<Table>(ksize_from_py(ksize), store_kmers, device, capacity_hint, deferred);
+        .def(py::init([](py::object ksize, bool store_kmers, int device, uint64_t capacity_hint, py::object deferred) {
+                 // deferred=None: OXLI_B200_DEFERRED=1 switches existing per-record scripts over without edits
+                 bool defer = false;
+                 if (deferred.is_none()) {
+                     const char *e = getenv("OXLI_B200_DEFERRED");
+                     defer = e && *e && strcmp(e, "0") != 0;
+                 } else defer = deferred.cast<bool>();
+                 return std::make_unique<Table>(ksize_from_py(ksize), store_kmers, device, capacity_hint, defer);
              }),
              py::arg("ksize"), py::arg("store_kmers") = false, py::kw_only(), py::arg("device") = 0,
-             py::arg("capacity_hint") = 0, py::arg("deferred") = false)
+             py::arg("capacity_hint") = 0, py::arg("deferred") = py::none())
+        .def_property_readonly("deferred", [](const Table &t) { return t.deferred; })
         .def("flush", &Table::sync, "send reads parked by deferred consume() calls to the GPU")
         .def("hash_kmer", &Table::hash_kmer, py::arg("kmer"))
         .def("unhash", [](const Table &t, uint64_t hv) {

@@ -337,3 +337,14 @@ def test_deferred_consume_matches_immediate(oxli, example_seq):
         d.consume("ACGTN" * 30, skip_bad_kmers=False)  # error mode is never deferred
     d.consume(reads[0]); d.flush()
     assert d.get(reads[0][:21]) == a.get(reads[0][:21]) + 1
+
+
+def test_deferred_default_comes_from_the_environment(oxli, monkeypatch):
+    monkeypatch.delenv("OXLI_B200_DEFERRED", raising=False)
+    assert oxli.KmerCountTable(21).deferred is False
+    monkeypatch.setenv("OXLI_B200_DEFERRED", "1")
+    t = oxli.KmerCountTable(21)
+    assert t.deferred is True and oxli.KmerCountTable(21, deferred=False).deferred is False
+    assert t.consume("ACGTACGTACGTACGTACGTACGTA") == 5 and 0 < len(t) <= 5
+    monkeypatch.setenv("OXLI_B200_DEFERRED", "0")
+    assert oxli.KmerCountTable(21).deferred is False
