@@ -7,13 +7,14 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstddef>
-#include <future>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -58,20 +59,21 @@ static const uint64_t kChunkBytes = [] { const char *e = getenv("OXLI_B200_CHUNK
 constexpr uint64_t kLaunchWindows = 64ull << 20;  // windows per consume launch (bounds the overflow list)
 constexpr uint64_t kSmallBatch = 1ull << 20;      // below this, reserve for the worst case up front
 constexpr uint64_t kMinCap = 1024;
+constexpr int kStageBufs = 4;  // host batches: chunks in flight between the copy stream and the kernels
 
 struct DeviceCtx {
     int dev = -1;
     int sms = 0;
     cudaStream_t stream = nullptr, copy = nullptr;
     std::mutex mu;
-    // double-buffered staging for host batches
-    uint8_t *d_stage[2] = {nullptr, nullptr};
-    uint8_t *h_stage[2] = {nullptr, nullptr};
-    uint64_t d_stage_cap[2] = {0, 0}, h_stage_cap[2] = {0, 0};
-    uint64_t *d_offs[2] = {nullptr, nullptr};
-    uint64_t *h_offs[2] = {nullptr, nullptr};
-    uint64_t offs_cap[2] = {0, 0};
-    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    // ring of staging buffers for host batches
+    uint8_t *d_stage[kStageBufs] = {};
+    uint8_t *h_stage[kStageBufs] = {};
+    uint64_t d_stage_cap[kStageBufs] = {}, h_stage_cap[kStageBufs] = {};
+    uint64_t *d_offs[kStageBufs] = {};
+    uint64_t *h_offs[kStageBufs] = {};
+    uint64_t offs_cap[kStageBufs] = {};
+    cudaEvent_t ev_ready[kStageBufs] = {};
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     cudaEvent_t ev_user0 = nullptr, ev_user1 = nullptr;
     // scratch
@@ -109,10 +111,7 @@ oxg_status get_ctx(int dev, DeviceCtx **out) {
         c->sms = prop.multiProcessorCount;
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            CU(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
-        }
+        for (int i = 0; i < kStageBufs; ++i) CU(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
         CU(cudaEventCreate(&c->ev_t0));
         CU(cudaEventCreate(&c->ev_t1));
         CU(cudaEventCreate(&c->ev_user0));
@@ -585,20 +584,27 @@ oxg_status oxg_hash_batch_device(oxg_table *t, const uint8_t *d_bases, const uin
     return OXG_OK;
 }
 
-// Host batch: stream [w_lo, w_hi) through the two staging buffers.
+// Host batch: stream [w_lo, w_hi) through a ring of kStageBufs staging buffers.  A producer
+// thread slices the read boundaries, stages pageable sources into pinned memory and queues the
+// H2D copies back to back on the copy stream, up to kStageBufs chunks ahead of the kernels; the
+// calling thread launches each chunk's kernels as its copy lands (run_span blocks until they
+// are done, which is also what frees the chunk's buffer).  With only one chunk in flight ahead
+// the copy engine idled between chunks and the step was 19 ms longer than its kernels.
 static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, const uint64_t *offsets,
                               uint64_t n_reads, uint64_t w_lo, uint64_t w_hi, uint64_t data_end,
-                              bool src_pinned, uint64_t *counted) {
+                              bool src_pinned, uint64_t *counted, const uint8_t *mapped = nullptr) {
+    // mapped != nullptr: device-usable alias of `bases` (pinned, mapped host memory); the kernels
+    // then read the bases in place over PCIe and only the read boundaries are copied
     DeviceCtx *c = t->ctx;
     const uint64_t k = t->k;
     if (w_hi <= w_lo) return OXG_OK;
     const uint64_t base0 = offsets[0];
     const uint64_t first = w_lo & ~(uint64_t)(kTileW - 1);
     const uint64_t n_chunks = (w_hi - first + kChunkBytes - 1) / kChunkBytes;
-    // staging sized to the batch (pinning 2 x 64 MiB costs a third of a second; a caller
+    // staging sized to the batch (pinning full chunks costs a third of a second; a caller
     // that hands over a few thousand reads should not pay it), full chunks once one is needed
     const uint64_t stage_bytes = std::min(pow2_at_least(std::max<uint64_t>(data_end - first, 1 << 20)), kChunkBytes) + 256 + 16;
-    for (int b = 0; b < (n_chunks > 1 ? 2 : 1); ++b) {
+    for (int b = 0; b < (int)std::min<uint64_t>(n_chunks, kStageBufs) && !mapped; ++b) {
         if (c->d_stage_cap[b] < stage_bytes) {
             CU(cudaStreamSynchronize(c->stream));
             if (c->d_stage[b]) CU(cudaFree(c->d_stage[b]));
@@ -614,59 +620,90 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
             c->h_stage_cap[b] = stage_bytes;
         }
     }
-    auto issue_copy = [&](uint64_t ci) -> oxg_status {
-        const int b = (int)(ci & 1);
-        const uint64_t lo = first + ci * kChunkBytes;
-        const uint64_t hi = std::min(data_end, lo + kChunkBytes + k - 1);
+    struct Slice { uint64_t lo, hi; const uint64_t *ob; uint64_t n_off; };
+    auto slice_of = [&](uint64_t ci) {
+        Slice s;
+        s.lo = first + ci * kChunkBytes;
+        s.hi = std::min(data_end, s.lo + kChunkBytes + k - 1);
         // reads whose boundaries can fall inside [lo, hi + 1]
-        const uint64_t *ob = std::lower_bound(offsets, offsets + n_reads + 1, base0 + lo + 1);
-        const uint64_t *oe = std::upper_bound(offsets, offsets + n_reads + 1, base0 + hi + 1);
-        const uint64_t n_off = (uint64_t)(oe - ob);
-        if (c->offs_cap[b] < n_off + 1) {
+        s.ob = std::lower_bound(offsets, offsets + n_reads + 1, base0 + s.lo + 1);
+        s.n_off = (uint64_t)(std::upper_bound(offsets, offsets + n_reads + 1, base0 + s.hi + 1) - s.ob);
+        return s;
+    };
+    // the previous use of buffer b (chunk ci - kStageBufs) is over: its kernels were waited for
+    auto issue_copy = [&](uint64_t ci) -> oxg_status {
+        const int b = (int)(ci % kStageBufs);
+        const Slice s = slice_of(ci);
+        if (c->offs_cap[b] < s.n_off + 1) {
+            CU(cudaStreamSynchronize(c->copy));
             if (c->d_offs[b]) CU(cudaFree(c->d_offs[b]));
             if (c->h_offs[b]) CU(cudaFreeHost(c->h_offs[b]));
             c->d_offs[b] = nullptr; c->h_offs[b] = nullptr; c->offs_cap[b] = 0;
-            const uint64_t ncap = std::max<uint64_t>(n_off + 1, 1 << 16);
+            const uint64_t ncap = std::max<uint64_t>(s.n_off + 1, 1 << 16);
             CU(cudaMalloc(&c->d_offs[b], ncap * 8));
             CU(cudaMallocHost(&c->h_offs[b], ncap * 8));
             c->offs_cap[b] = ncap;
         }
-        CU(cudaEventSynchronize(c->ev_free[b]));
-        for (uint64_t i = 0; i < n_off; ++i) c->h_offs[b][i] = ob[i] - base0;  // batch-relative positions
-        c->h_offs[b][n_off] = ~0ULL >> 1;  // sentinel keeps n_off >= 1
-        const uint8_t *src = bases + base0 + lo;
-        if (!src_pinned) { memcpy(c->h_stage[b], src, hi - lo); src = c->h_stage[b]; }
-        CU(cudaMemcpyAsync(c->d_stage[b], src, hi - lo, cudaMemcpyHostToDevice, c->copy));
-        CU(cudaMemcpyAsync(c->d_offs[b], c->h_offs[b], (n_off + 1) * 8, cudaMemcpyHostToDevice, c->copy));
+        for (uint64_t i = 0; i < s.n_off; ++i) c->h_offs[b][i] = s.ob[i] - base0;  // batch-relative positions
+        c->h_offs[b][s.n_off] = ~0ULL >> 1;  // sentinel keeps n_off >= 1
+        const uint8_t *src = bases + base0 + s.lo;
+        if (!src_pinned) { memcpy(c->h_stage[b], src, s.hi - s.lo); src = c->h_stage[b]; }
+        if (!mapped) CU(cudaMemcpyAsync(c->d_stage[b], src, s.hi - s.lo, cudaMemcpyHostToDevice, c->copy));
+        CU(cudaMemcpyAsync(c->d_offs[b], c->h_offs[b], (s.n_off + 1) * 8, cudaMemcpyHostToDevice, c->copy));
         CU(cudaEventRecord(c->ev_ready[b], c->copy));
         return OXG_OK;
     };
-    TRY(issue_copy(0));
-    for (uint64_t ci = 0; ci < n_chunks; ++ci) {
-        const int b = (int)(ci & 1);
-        const uint64_t lo = first + ci * kChunkBytes;
-        const uint64_t hi = std::min(data_end, lo + kChunkBytes + k - 1);
-        const uint64_t *ob = std::lower_bound(offsets, offsets + n_reads + 1, base0 + lo + 1);
-        const uint64_t *oe = std::upper_bound(offsets, offsets + n_reads + 1, base0 + hi + 1);
-        const uint64_t n_off = (uint64_t)(oe - ob) + 1;
+    auto run_chunk = [&](uint64_t ci) -> oxg_status {
+        const int b = (int)(ci % kStageBufs);
+        const Slice s = slice_of(ci);
         CU(cudaStreamWaitEvent(c->stream, c->ev_ready[b], 0));
-        // run_span blocks on the stream after every launch, so the next chunk's staging
-        // (host memcpy into pinned memory + H2D on the copy stream) runs on a helper
-        // thread and overlaps this chunk's kernels
-        // (also for pinned sources: slicing the offsets is host work that should not delay the launch)
-        std::future<oxg_status> next;
-        if (ci + 1 < n_chunks)
-            next = std::async(std::launch::async, [&, ci] { cudaSetDevice(c->dev); return issue_copy(ci + 1); });
-        oxg_status st = run_span(t, mode, c->d_stage[b], lo, std::max(lo, w_lo), std::min(w_hi, lo + kChunkBytes), hi,
-                                 c->d_offs[b], n_off, nullptr, counted);
-        if (next.valid()) {
-            oxg_status st2 = next.get();
-            if (st == OXG_OK && st2 != OXG_OK) st = fail(st2, "staging copy failed");
-        }
-        TRY(st);
-        CU(cudaEventRecord(c->ev_free[b], c->stream));
+        return run_span(t, mode, mapped ? mapped + base0 + s.lo : c->d_stage[b], s.lo, std::max(s.lo, w_lo),
+                        std::min(w_hi, s.lo + kChunkBytes), s.hi, c->d_offs[b], s.n_off + 1, nullptr, counted);
+    };
+    if (n_chunks == 1) {
+        TRY(issue_copy(0));
+        return run_chunk(0);
     }
-    return OXG_OK;
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t issued = 0, done = 0;  // chunks whose copies are queued / whose kernels have finished
+    bool stop = false;
+    oxg_status producer_status = OXG_OK;
+    std::thread producer([&] {
+        cudaSetDevice(c->dev);
+        for (uint64_t ci = 0; ci < n_chunks; ++ci) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || ci < done + kStageBufs; });
+                if (stop) return;
+            }
+            const oxg_status st = issue_copy(ci);
+            std::lock_guard<std::mutex> lk(mu);
+            if (st != OXG_OK) { producer_status = st; issued = n_chunks; cv.notify_all(); return; }
+            issued = ci + 1;
+            cv.notify_all();
+        }
+    });
+    oxg_status st = OXG_OK;
+    for (uint64_t ci = 0; ci < n_chunks && st == OXG_OK; ++ci) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return issued > ci; });
+            if (producer_status != OXG_OK) { st = fail(producer_status, "staging copy failed"); break; }
+        }
+        st = run_chunk(ci);
+        std::lock_guard<std::mutex> lk(mu);
+        done = ci + 1;
+        cv.notify_all();
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+        cv.notify_all();
+    }
+    producer.join();
+    if (st != OXG_OK) cudaStreamSynchronize(c->copy);  // nothing may still be writing the staging buffers
+    return st;
 }
 
 oxg_status oxg_consume_batch(oxg_table *t, const uint8_t *bases, const uint64_t *offsets,
@@ -688,10 +725,13 @@ oxg_status oxg_consume_batch(oxg_table *t, const uint8_t *bases, const uint64_t 
     cudaPointerAttributes attr{};
     bool pinned = cudaPointerGetAttributes(&attr, bases) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
+    static const bool zero_copy = [] { const char *e = getenv("OXLI_B200_ZEROCOPY"); return e && *e && strcmp(e, "0") != 0; }();
+    const uint8_t *mapped = pinned && zero_copy && attr.devicePointer ? static_cast<const uint8_t *>(attr.devicePointer) : nullptr;
+    if (mapped && ((reinterpret_cast<uintptr_t>(mapped) + offsets[0]) & 15)) mapped = nullptr;  // the kernels copy 16-byte units
     uint64_t counted = 0;
     oxg_status ret = OXG_OK;
     if (skip_bad) {
-        TRY(stream_span(t, kModeCount, bases, offsets, n_reads, 0, n_win, total, pinned, &counted));
+        TRY(stream_span(t, kModeCount, bases, offsets, n_reads, 0, n_win, total, pinned, &counted, mapped));
     } else {
         t->h_ctrl->first_bad = ~0ULL;
         CU(cudaMemcpyAsync(&t->d_ctrl->first_bad, &t->h_ctrl->first_bad, 8, cudaMemcpyHostToDevice, c->stream));

@@ -138,12 +138,61 @@ __device__ __forceinline__ void stage16(const ConsumeParams &p, uint64_t w0, int
 
 // ---- cp.async (LDGSTS): global -> shared without passing through registers ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, uint32_t src_bytes) {
+#ifndef OXG_STREAM_EVICT_FIRST
+#define OXG_STREAM_EVICT_FIRST 1
+#endif
+// The bases are read once; the table is what should stay in L2.  The streaming copies carry
+// an evict-first policy so that 1.5 GB of reads per step do not push table sectors out.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, uint32_t src_bytes, uint64_t pol) {
+#if OXG_STREAM_EVICT_FIRST
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
+// ---- bulk async copy (the TMA engine's 1-D form) + mbarrier: one lane moves a whole tile ----
+#ifndef OXG_BULK_STAGE
+#define OXG_BULK_STAGE 1
+#endif
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+#if OXG_STREAM_EVICT_FIRST
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+#else
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+#endif
+}
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -304,13 +353,34 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeRoute ? 2 : OXG_MIN_CTA
     bool tiles_left = true;
     bool absorb_left = MODE == kModeRoute && p.n_absorb > 0;
 
-    auto prefetch_raw = [&](uint64_t tile, uint8_t *dst) {
+    const uint64_t stream_policy = l2_evict_first_policy();
+#if OXG_BULK_STAGE
+    // one transaction barrier per raw buffer of this warp; a phase = one tile's bytes
+    __shared__ __align__(8) uint64_t s_bar_all[kWarps][2];
+    uint64_t *s_bar = s_bar_all[warp];
+    uint32_t bar_parity = 0;  // bit b: parity to wait for on buffer b
+    if (lane == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); mbar_fence_init(); }
+    __syncwarp();
+    // Bytes past data_end are masked as bad whatever they hold (stage16_raw), so a tile at the
+    // end of the data copies whole 16-byte units (at most 15 bytes past the end, inside the
+    // same aligned unit as the last base) and leaves the rest of the buffer as it was.
+    auto prefetch_raw = [&](uint64_t tile, uint8_t *dst, int b) {
+        if (lane == 0) {
+            const uint64_t g = p.tile_base + tile * kWarpTile;
+            const uint32_t n = g >= p.data_end ? 0u : (uint32_t)min((uint64_t)BL, (uint64_t)((p.data_end - g + 15) & ~15ull));
+            mbar_arrive_expect_tx(&s_bar[b], n);
+            if (n) bulk_g2s(dst, p.bases + (g - p.g0), n, &s_bar[b], stream_policy);
+        }
+    };
+#else
+    auto prefetch_raw = [&](uint64_t tile, uint8_t *dst, int) {
         if (lane < NV) {
             const uint64_t g = p.tile_base + tile * kWarpTile + 16ull * lane;
             const uint32_t n = g >= p.data_end ? 0u : (uint32_t)min((uint64_t)16, p.data_end - g);
-            cp_async16_zfill(dst + 16 * lane, n ? p.bases + (g - p.g0) : p.bases, n);
+            cp_async16_zfill(dst + 16 * lane, n ? p.bases + (g - p.g0) : p.bases, n, stream_policy);
         }
     };
+#endif
     auto prefetch_offsets = [&](uint64_t first, uint64_t *dst) {
         const uint64_t r = first + lane;
         if (r < p.n_off) cp_async8(dst + lane, p.offsets + r);
@@ -335,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeRoute ? 2 : OXG_MIN_CTA
     uint64_t t_cur = next_tile_id(), t_nxt = next_tile_id();
     int buf = 0;
     if (t_cur < p.n_tiles) {
-        prefetch_raw(t_cur, s_raw_all[warp][0]);
+        prefetch_raw(t_cur, s_raw_all[warp][0], 0);
         prefetch_offsets(p.tile_first[t_cur], s_off_all[warp][0]);
     }
     cp_async_commit();
@@ -373,6 +443,9 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeRoute ? 2 : OXG_MIN_CTA
         late = t * 4 >= p.n_tiles * 3;
         if (MODE == kModeFirstBad && w0 > __ldcg(&p.table.ctrl->first_bad)) {
             // a bad window before this tile is already known: nothing later can be the first
+#if OXG_BULK_STAGE
+            mbar_wait(&s_bar[buf], (bar_parity >> buf) & 1u);  // this tile's copy is in flight: let it land
+#endif
             tiles_left = false; cp_async_wait<0>(); continue;
         }
         uint8_t *s_raw = s_raw_all[warp][buf];
@@ -383,10 +456,14 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeRoute ? 2 : OXG_MIN_CTA
         uint64_t tf_next = 0;
         if (t_nxt < p.n_tiles) {
             tf_next = __ldg(p.tile_first + t_nxt);
-            prefetch_raw(t_nxt, s_raw_all[warp][buf ^ 1]);
+            prefetch_raw(t_nxt, s_raw_all[warp][buf ^ 1], buf ^ 1);
         }
         cp_async_commit();
         cp_async_wait<1>();  // everything issued before this iteration (this tile's bytes and boundaries) has landed
+#if OXG_BULK_STAGE
+        mbar_wait(&s_bar[buf], (bar_parity >> buf) & 1u);
+        bar_parity ^= 1u << buf;
+#endif
         if (lane < NE) s_end[lane] = 0;
         __syncwarp();
 
