@@ -258,7 +258,21 @@ oxg_status grow_to_fit(oxg_table *t, uint64_t keys) {
 
 oxg_status reserve_keys(oxg_table *t, uint64_t extra) { return grow_to_fit(t, t->size + extra); }
 
-bool specialised_k(uint32_t k) { return k == 21 || k == 31; }
+// k values with a compile-time specialised consume kernel (everything else, up to 255, runs
+// the generic kernel at a third to a fifth of the speed); the sharded route mode only for the
+// two k the reference's workloads use
+#define OXG_FOR_EACH_K(X) X(15) X(17) X(19) X(20) X(21) X(23) X(24) X(25) X(27) X(29) X(31) X(32)
+constexpr bool route_k(int k) { return k == 21 || k == 31; }
+bool specialised_k(uint32_t k) {
+    switch (k) {
+#define OXG_K_TRUE(KK) case KK:
+        OXG_FOR_EACH_K(OXG_K_TRUE)
+#undef OXG_K_TRUE
+        return true;
+    default:
+        return false;
+    }
+}
 uint32_t tile_width(uint32_t k) { return specialised_k(k) ? kWarpTile : kTileW; }
 
 template <int MODE>
@@ -275,17 +289,20 @@ oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
     switch (k) {
 #define OXG_CASE(KK)                                                                              \
     case KK: {                                                                                    \
-        const size_t dyn = consume_dyn_smem(MODE);                                                \
-        static bool attr_set = false;                                                             \
-        if (dyn && !attr_set) {                                                                   \
-            CU(cudaFuncSetAttribute(consume_kernel<KK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-            attr_set = true;                                                                      \
+        if constexpr (MODE == kModeRoute && !route_k(KK)) {                                       \
+            return fail(OXG_ERR_INVALID, "sharded routing is built for k = 21 and 31 only");      \
+        } else {                                                                                  \
+            const size_t dyn = consume_dyn_smem(MODE);                                            \
+            static std::atomic<uint64_t> attr_set{0}; /* one bit per device */                   \
+            if (dyn && !((attr_set.load() >> c->dev) & 1)) {                                      \
+                CU(cudaFuncSetAttribute(consume_kernel<KK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
+                attr_set.fetch_or(1ull << c->dev);                                                \
+            }                                                                                     \
+            consume_kernel<KK, MODE><<<grid_of((const void *)consume_kernel<KK, MODE>, dyn), kThreads, dyn, c->stream>>>(p); \
         }                                                                                         \
-        consume_kernel<KK, MODE><<<grid_of((const void *)consume_kernel<KK, MODE>, dyn), kThreads, dyn, c->stream>>>(p); \
         break;                                                                                    \
     }
-        OXG_CASE(21)
-        OXG_CASE(31)
+        OXG_FOR_EACH_K(OXG_CASE)
 #undef OXG_CASE
     default:
         if (MODE == kModeRoute) return fail(OXG_ERR_INVALID, "sharded routing is built for k = 21 and 31 only");
@@ -1206,7 +1223,7 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
     if (self_rank < 0 || self_rank >= n_ranks) return fail(OXG_ERR_INVALID, "self_rank out of range");
     if (n_absorb < 0 || n_absorb > kMaxRanks) return fail(OXG_ERR_INVALID, "at most %d absorb segments", kMaxRanks);
     if (base_hi < base_lo) return fail(OXG_ERR_INVALID, "base_hi < base_lo");
-    if (!specialised_k(t->k)) return fail(OXG_ERR_INVALID, "sharded routing is built for k = 21 and 31 only");
+    if (!route_k((int)t->k)) return fail(OXG_ERR_INVALID, "sharded routing is built for k = 21 and 31 only");
     if (local_counted) *local_counted = 0;
     if (absorbed) *absorbed = 0;
     const uint64_t k = t->k;

@@ -96,7 +96,7 @@ def test_example_fa_goldens(capi, example_seq, goldens):
         assert (s["len"], s["sum"], s["min"], s["max"]) == (g["distinct"], g["sum"], g["min"], g["max"])
 
 
-@pytest.mark.parametrize("k", [4, 16, 21, 31, 32, 33, 51])
+@pytest.mark.parametrize("k", [4, 15, 16, 19, 21, 24, 25, 29, 31, 32, 33, 51])
 def test_consume_ragged_batch_skip_mode(capi, k):
     rng = np.random.default_rng(100 + k)
     bases, offs = ragged_batch(rng, 4000, 260, p_bad=0.01)
@@ -125,7 +125,7 @@ def test_consume_incremental_equals_batch(capi, k):
     assert_same_table(many, ora)
 
 
-@pytest.mark.parametrize("k", [5, 21, 31, 35])
+@pytest.mark.parametrize("k", [5, 17, 21, 27, 31, 35])
 def test_consume_error_mode(capi, k):
     rng = np.random.default_rng(k)
     # clean reads, then one read with a bad byte in the middle, then more reads
