@@ -261,7 +261,7 @@ oxg_status reserve_keys(oxg_table *t, uint64_t extra) { return grow_to_fit(t, t-
 // k values with a compile-time specialised consume kernel (everything else, up to 255, runs
 // the generic kernel at a third to a fifth of the speed); the sharded route mode only for the
 // two k the reference's workloads use
-#define OXG_FOR_EACH_K(X) X(15) X(17) X(19) X(20) X(21) X(23) X(24) X(25) X(27) X(29) X(31) X(32)
+#define OXG_FOR_EACH_K(X) X(15) X(17) X(19) X(20) X(21) X(23) X(24) X(25) X(27) X(29) X(31) X(32) X(41) X(51) X(63)
 constexpr bool route_k(int k) { return k == 21 || k == 31; }
 bool specialised_k(uint32_t k) {
     switch (k) {

@@ -301,8 +301,8 @@ __device__ __forceinline__ void slow_round(const TableView &tv, SlowQueue &q, bo
 // first version used 2048-window CTA tiles; ncu showed 30 % of all stall samples
 // at the CTA barrier waiting for the one warp stuck in a long probe.)
 template <int K, int MODE>
-__global__ void __launch_bounds__(kThreads, MODE == kModeRoute ? 2 : OXG_MIN_CTAS) consume_kernel(const ConsumeParams p) {
-    static_assert(K >= 1 && K <= 32, "specialised kernel covers k <= 32");
+__global__ void __launch_bounds__(kThreads, (MODE == kModeRoute || K > 32) ? 2 : OXG_MIN_CTAS) consume_kernel(const ConsumeParams p) {
+    static_assert(K >= 1 && K <= 64, "specialised kernel covers k <= 64");
     constexpr int Q = 8 * ((K + 7 + 7) / 8);  // bytes a thread pulls per strand
     constexpr int BL = ((kWarpTile - 8 + Q) + 15) / 16 * 16;
     constexpr int NV = BL / 16;
@@ -487,16 +487,30 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeRoute ? 2 : OXG_MIN_CTA
         const int p0 = lane * kWPT;
         const uint32_t *bad32 = reinterpret_cast<const uint32_t *>(s_bad);
         const int wi = p0 >> 5, sh = p0 & 31;
+        // bits [p0, p0 + 7 + K) of the two masks: two 32-bit words hold them up to K = 33,
+        // three up to K = 64 (sh is 0, 8, 16 or 24)
         const uint64_t mb = (((uint64_t)bad32[wi + 1] << 32) | bad32[wi]) >> sh;
         const uint64_t me = (((uint64_t)s_end[wi + 1] << 32) | s_end[wi]) >> sh;
+        uint64_t mb_hi = 0, me_hi = 0;  // bits 64.. of the same, K > 33 only
+        if constexpr (K > 33) {
+            mb_hi = ((uint64_t)bad32[wi + 2] << 32) >> sh;  // its bit i is mask bit 32 + i
+            me_hi = ((uint64_t)s_end[wi + 2] << 32) >> sh;
+        }
         const uint64_t gp0 = w0 + p0;
 
         uint32_t valid = 0;
 #pragma unroll
         for (int j = 0; j < kWPT; ++j) {
             const bool in_range = gp0 + j >= p.w_lo && gp0 + j < p.w_hi;
-            const bool in_read = ((me >> j) & MK1) == 0;
-            const bool clean = ((mb >> j) & MK) == 0;
+            uint64_t vb = mb >> j, ve = me >> j;
+            if constexpr (K > 33) {
+                // mask bits [j, j + 64): the low 64 - sh come from the first two words, the rest
+                // from the third, whose bit i is mask bit 32 + i
+                vb = (mb | (mb_hi << 32)) >> j | (j ? (mb_hi >> 32) << (64 - j) : 0);
+                ve = (me | (me_hi << 32)) >> j | (j ? (me_hi >> 32) << (64 - j) : 0);
+            }
+            const bool in_read = (ve & MK1) == 0;
+            const bool clean = (vb & MK) == 0;
             if (MODE == kModeFirstBad) {
                 if (in_range && in_read && !clean && gp0 + j + K <= p.data_end)
                     first_bad = min(first_bad, gp0 + j);

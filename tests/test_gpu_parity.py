@@ -45,7 +45,7 @@ def test_hash_windows_example_fa(capi, example_seq, k):
     assert got.shape == want.shape and np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 20, 21, 22, 24, 31, 32, 33, 40, 51, 64, 100, 255])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 20, 21, 22, 24, 31, 32, 33, 40, 41, 51, 63, 64, 100, 255])
 def test_hash_windows_every_k_with_junk(capi, k):
     rng = np.random.default_rng(k)
     bases, _ = ragged_batch(rng, 1, 9000, p_bad=0.004, p_lower=0.2, p_empty=0.0)
@@ -96,7 +96,7 @@ def test_example_fa_goldens(capi, example_seq, goldens):
         assert (s["len"], s["sum"], s["min"], s["max"]) == (g["distinct"], g["sum"], g["min"], g["max"])
 
 
-@pytest.mark.parametrize("k", [4, 15, 16, 19, 21, 24, 25, 29, 31, 32, 33, 51])
+@pytest.mark.parametrize("k", [4, 15, 16, 19, 21, 24, 25, 29, 31, 32, 33, 41, 51, 63, 64])
 def test_consume_ragged_batch_skip_mode(capi, k):
     rng = np.random.default_rng(100 + k)
     bases, offs = ragged_batch(rng, 4000, 260, p_bad=0.01)
@@ -125,7 +125,7 @@ def test_consume_incremental_equals_batch(capi, k):
     assert_same_table(many, ora)
 
 
-@pytest.mark.parametrize("k", [5, 17, 21, 27, 31, 35])
+@pytest.mark.parametrize("k", [5, 17, 21, 27, 31, 35, 51, 63])
 def test_consume_error_mode(capi, k):
     rng = np.random.default_rng(k)
     # clean reads, then one read with a bad byte in the middle, then more reads
