@@ -679,7 +679,9 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
     };
     if (n_chunks == 1) {
         TRY(issue_copy(0));
-        return run_chunk(0);
+        TRY(run_chunk(0));
+        if (mode != kModeCount) TRY(pull_ctrl(t));  // see below: the buffer is free again when this returns
+        return OXG_OK;
     }
     std::mutex mu;
     std::condition_variable cv;
@@ -709,9 +711,18 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
             if (producer_status != OXG_OK) { st = fail(producer_status, "staging copy failed"); break; }
         }
         st = run_chunk(ci);
+        bool found = false;
+        if (st == OXG_OK && mode != kModeCount) {
+            // only counting launches are waited for inside run_span; the buffer must not be
+            // refilled before this chunk's kernel has read it.  A pre-scan that has found its
+            // bad window needs no later chunk.
+            st = pull_ctrl(t);
+            found = st == OXG_OK && mode == kModeFirstBad && t->h_ctrl->first_bad != ~0ULL;
+        }
         std::lock_guard<std::mutex> lk(mu);
         done = ci + 1;
         cv.notify_all();
+        if (found) break;
     }
     {
         std::lock_guard<std::mutex> lk(mu);
@@ -719,7 +730,9 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
         cv.notify_all();
     }
     producer.join();
-    if (st != OXG_OK) cudaStreamSynchronize(c->copy);  // nothing may still be writing the staging buffers
+    // a call that stopped early (error, or pre-scan hit) may have copies queued that nobody will
+    // wait for: drain them before the staging buffers are used again
+    if (st != OXG_OK || mode != kModeCount) cudaStreamSynchronize(c->copy);
     return st;
 }
 
