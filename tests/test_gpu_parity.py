@@ -257,6 +257,41 @@ def test_multi_chunk_streaming(capi):
     assert np.array_equal(gk, ok) and np.array_equal(gv, 2 * ov)
 
 
+def test_error_mode_across_host_chunks(capi):
+    """Error mode on a host batch of three staging chunks whose first bad k-mer lies in the second:
+    the pre-scan stops there, and the counted prefix equals skip mode on exactly that prefix
+    (src/lib.rs:586-600: everything before the failing window is counted, then the error)."""
+    k, L, n, G = 31, 151, 900_000, 300_000
+    d_bases = capi.device_alloc(n * L + 64)
+    try:
+        capi.synth_reads_device(d_bases, n, L, G, seed=5)
+        bases = np.empty(n * L, dtype=np.uint8)
+        capi.d2h(bases, d_bases)
+    finally:
+        capi.device_free(d_bases)
+    offs = uniform_offsets(n, L)
+    r_bad, at = 500_000, 60                      # byte 75.5 M: second 64 MiB chunk
+    bases[r_bad * L + at] = ord("N")
+    bases[(r_bad + 300_000) * L + 7] = ord("N")  # a later one, in the third chunk, must not matter
+    for src in ("pageable", "pinned"):
+        buf = bases
+        if src == "pinned":
+            buf = capi.pinned_empty(bases.nbytes)
+            buf[:] = bases
+        t = capi.Table(k)
+        st, total, er, ep = t.consume_batch(buf, offs, skip_bad=False)
+        assert (st, er, ep) == (capi.ERR_BAD_KMER, r_bad, at - k + 1)
+        ref = capi.Table(k)
+        cut = r_bad * L + at                     # the clean prefix of the failing read is a read of its own
+        pre_offs = np.concatenate([offs[: r_bad + 1], np.array([cut], dtype=np.uint64)])
+        st2, want, er2, _ = ref.consume_batch(buf[:cut], pre_offs, skip_bad=True)
+        assert (st2, er2) == (0, -1) and total == want == r_bad * (L - k + 1) + (at - k + 1)
+        a, b = t.export(1), ref.export(1)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        if src == "pinned":
+            capi.pinned_free(buf)
+
+
 # ------------------------------------------------------------- device-resident
 
 def test_device_resident_consume_and_generator(capi):
