@@ -14,8 +14,9 @@ EXT = os.path.join(HERE, "_oxli" + (sysconfig.get_config_var("EXT_SUFFIX") or ".
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJ = os.path.join(HERE, "_obj")
 
 
 def _stale(target: str, sources: list[str]) -> bool:
@@ -33,13 +34,47 @@ def _sources(exts: tuple[str, ...]) -> list[str]:
     return out
 
 
+def specialised_ks() -> list[int]:
+    """The k values of csrc/klist.h (one translation unit each)."""
+    import re
+
+    text = open(os.path.join(CSRC, "klist.h")).read()
+    body = text[text.index("#define OXG_FOR_EACH_K"):text.index("#define OXG_ROUTE_K")]
+    return [int(m) for m in re.findall(r"X\((\d+)\)", body)]
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
-    srcs = _sources((".cu", ".cuh"))
-    if force or _stale(LIB, srcs):
-        cmd = ["nvcc", *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "capi.cu")]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        subprocess.check_call(cmd)
+    """capi.cu + one consume_inst.cu object per specialised k, compiled in parallel, linked into
+    one shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    srcs = _sources((".cu", ".cuh", ".h"))
+    if not force and not _stale(LIB, srcs):
+        return LIB  # up to date (the objects do not travel to the GPU box; the library does)
+    os.makedirs(OBJ, exist_ok=True)
+    jobs = [(os.path.join(OBJ, "capi.o"), os.path.join(CSRC, "capi.cu"), [])]
+    for k in specialised_ks():
+        jobs.append((os.path.join(OBJ, f"consume_k{k}.o"), os.path.join(CSRC, "consume_inst.cu"), [f"-DOXG_INST_K={k}"]))
+    wanted = {j[0] for j in jobs}
+    for f in os.listdir(OBJ):  # objects of k values that left the list
+        if os.path.join(OBJ, f) not in wanted:
+            os.remove(os.path.join(OBJ, f))
+
+    def compile_one(job):
+        obj, src, defs = job
+        if force or _stale(obj, srcs):
+            cmd = ["nvcc", *NVCC_FLAGS, *defs, "-c", "-o", obj, src]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            subprocess.check_call(cmd)
+            return True
+        return False
+
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as pool:
+        rebuilt = list(pool.map(compile_one, jobs))
+    if any(rebuilt) or not os.path.exists(LIB):
+        subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-o", LIB, *[j[0] for j in jobs]])
     return LIB
 
 

@@ -21,6 +21,7 @@
 
 #include "../../include/oxli_b200.h"
 #include "consume.cuh"
+#include "klist.h"
 #include "tableops.cuh"
 
 using namespace oxg;
@@ -258,21 +259,22 @@ oxg_status grow_to_fit(oxg_table *t, uint64_t keys) {
 
 oxg_status reserve_keys(oxg_table *t, uint64_t extra) { return grow_to_fit(t, t->size + extra); }
 
-// k values with a compile-time specialised consume kernel (everything else, up to 255, runs
-// the generic kernel at a third to a fifth of the speed); the sharded route mode only for the
-// two k the reference's workloads use
-#define OXG_FOR_EACH_K(X) X(15) X(17) X(19) X(20) X(21) X(23) X(24) X(25) X(27) X(29) X(31) X(32) X(41) X(51) X(63)
-constexpr bool route_k(int k) { return k == 21 || k == 31; }
-bool specialised_k(uint32_t k) {
+// k values with a compile-time specialised consume kernel: klist.h.  Each lives in its own
+// translation unit (consume_inst.cu) and is reached through its entry function.
+#define OXG_DECLARE_ENTRY(KK) extern "C" const void *oxg_consume_entry_##KK(int mode);
+OXG_FOR_EACH_K(OXG_DECLARE_ENTRY)
+#undef OXG_DECLARE_ENTRY
+constexpr bool route_k(int k) { return OXG_ROUTE_K(k); }
+const void *specialised_entry(uint32_t k, int mode) {
     switch (k) {
-#define OXG_K_TRUE(KK) case KK:
-        OXG_FOR_EACH_K(OXG_K_TRUE)
-#undef OXG_K_TRUE
-        return true;
+#define OXG_K_ENTRY(KK) case KK: return oxg_consume_entry_##KK(mode);
+        OXG_FOR_EACH_K(OXG_K_ENTRY)
+#undef OXG_K_ENTRY
     default:
-        return false;
+        return nullptr;
     }
 }
+bool specialised_k(uint32_t k) { return specialised_entry(k, kModeCount) != nullptr; }
 uint32_t tile_width(uint32_t k) { return specialised_k(k) ? kWarpTile : kTileW; }
 
 template <int MODE>
@@ -286,25 +288,21 @@ oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
         const uint64_t work = p.n_tiles + (MODE == kModeRoute ? p.absorb_first[p.n_absorb] : 0);
         return (int)std::max<uint64_t>(1, std::min<uint64_t>((work + tiles_per_cta - 1) / tiles_per_cta, (uint64_t)c->sms * per_sm));
     };
-    switch (k) {
-#define OXG_CASE(KK)                                                                              \
-    case KK: {                                                                                    \
-        if constexpr (MODE == kModeRoute && !route_k(KK)) {                                       \
-            return fail(OXG_ERR_INVALID, "sharded routing is built for k = 21 and 31 only");      \
-        } else {                                                                                  \
-            const size_t dyn = consume_dyn_smem(MODE);                                            \
-            static std::atomic<uint64_t> attr_set{0}; /* one bit per device */                   \
-            if (dyn && !((attr_set.load() >> c->dev) & 1)) {                                      \
-                CU(cudaFuncSetAttribute(consume_kernel<KK, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); \
-                attr_set.fetch_or(1ull << c->dev);                                                \
-            }                                                                                     \
-            consume_kernel<KK, MODE><<<grid_of((const void *)consume_kernel<KK, MODE>, dyn), kThreads, dyn, c->stream>>>(p); \
-        }                                                                                         \
-        break;                                                                                    \
-    }
-        OXG_FOR_EACH_K(OXG_CASE)
-#undef OXG_CASE
-    default:
+    if (const void *fn = specialised_entry(t->k, MODE)) {
+        const size_t dyn = consume_dyn_smem(MODE);
+        if (dyn) {  // static + dynamic shared memory may pass 48 KB: opt in once per function and device
+            static std::mutex attr_mu;
+            static std::vector<std::pair<const void *, int>> attr_done;
+            std::lock_guard<std::mutex> lk(attr_mu);
+            const std::pair<const void *, int> key{fn, c->dev};
+            if (std::find(attr_done.begin(), attr_done.end(), key) == attr_done.end()) {
+                CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                attr_done.push_back(key);
+            }
+        }
+        void *args[] = {const_cast<ConsumeParams *>(&p)};
+        CU(cudaLaunchKernel(fn, dim3(grid_of(fn, dyn)), dim3(kThreads), args, dyn, c->stream));
+    } else {
         if (MODE == kModeRoute) return fail(OXG_ERR_INVALID, "sharded routing is built for k = 21 and 31 only");
         if constexpr (MODE != kModeRoute) {
             const size_t smem = generic_smem_bytes(k);

@@ -82,7 +82,7 @@ struct ConsumeParams {
     int n_absorb;
 };
 
-__global__ void tile_first_kernel(const uint64_t *__restrict__ offsets, uint64_t n_off,
+static __global__ void tile_first_kernel(const uint64_t *__restrict__ offsets, uint64_t n_off,
                                   uint64_t tile_base, uint64_t n_tiles, uint32_t tile_w,
                                   uint64_t *__restrict__ tile_first) {
     uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;

@@ -125,7 +125,7 @@ def test_consume_incremental_equals_batch(capi, k):
     assert_same_table(many, ora)
 
 
-@pytest.mark.parametrize("k", [5, 17, 21, 27, 31, 35, 51, 63])
+@pytest.mark.parametrize("k", [5, 17, 21, 27, 31, 35, 40, 51, 63])
 def test_consume_error_mode(capi, k):
     rng = np.random.default_rng(k)
     # clean reads, then one read with a bad byte in the middle, then more reads
