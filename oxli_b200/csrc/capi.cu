@@ -14,6 +14,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -686,7 +687,7 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
     uint64_t issued = 0, done = 0;  // chunks whose copies are queued / whose kernels have finished
     bool stop = false;
     oxg_status producer_status = OXG_OK;
-    std::thread producer([&] {
+    auto produce = [&] {
         cudaSetDevice(c->dev);
         for (uint64_t ci = 0; ci < n_chunks; ++ci) {
             {
@@ -700,7 +701,22 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
             issued = ci + 1;
             cv.notify_all();
         }
-    });
+    };
+    std::thread producer;
+    try {
+        producer = std::thread(produce);
+    } catch (const std::system_error &) {
+        // no helper thread to be had: stage and run the chunks in turn
+        for (uint64_t ci = 0; ci < n_chunks; ++ci) {
+            TRY(issue_copy(ci));
+            TRY(run_chunk(ci));
+            if (mode != kModeCount) {
+                TRY(pull_ctrl(t));
+                if (mode == kModeFirstBad && t->h_ctrl->first_bad != ~0ULL) break;
+            }
+        }
+        return OXG_OK;
+    }
     oxg_status st = OXG_OK;
     for (uint64_t ci = 0; ci < n_chunks && st == OXG_OK; ++ci) {
         {
