@@ -52,3 +52,14 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in text and "oxli_oracle" not in text, f
+
+
+def test_specialised_k_list_is_sane():
+    """csrc/klist.h drives both the build (one translation unit per k) and the dispatch in capi.cu."""
+    from oxli_b200 import _build
+
+    ks = _build.specialised_ks()
+    assert ks == sorted(set(ks)) and all(1 <= k <= 64 for k in ks)
+    assert {21, 31}.issubset(ks)  # the k values of BASELINE.json's configs; the only ones the route mode is built for
+    text = open(os.path.join(_build.CSRC, "capi.cu")).read()
+    assert "OXG_FOR_EACH_K(OXG_K_ENTRY)" in text and '#include "klist.h"' in text
