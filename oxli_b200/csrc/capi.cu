@@ -57,7 +57,17 @@ oxg_status fail(oxg_status st, const char *fmt, ...) {
     } while (0)
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
-static const uint64_t kChunkBytes = [] { const char *e = getenv("OXLI_B200_CHUNK_MB"); return (e ? (uint64_t)atoi(e) : 64ull) << 20; }();  // host->device streaming granule
+// host->device streaming granule: OXLI_B200_CHUNK_MB in 1..1024, anything else means the default
+static const uint64_t kChunkBytes = [] {
+    const char *e = getenv("OXLI_B200_CHUNK_MB");
+    long mb = 64;
+    if (e && *e) {
+        char *end = nullptr;
+        const long v = strtol(e, &end, 10);
+        if (end && *end == '\0' && v >= 1 && v <= 1024) mb = v;
+    }
+    return (uint64_t)mb << 20;
+}();
 constexpr uint64_t kLaunchWindows = 64ull << 20;  // windows per consume launch (bounds the overflow list)
 constexpr uint64_t kSmallBatch = 1ull << 20;      // below this, reserve for the worst case up front
 constexpr uint64_t kMinCap = 1024;
@@ -81,6 +91,7 @@ struct DeviceCtx {
     // scratch
     uint64_t *d_tile_first = nullptr; uint64_t tile_first_cap = 0;
     uint64_t *d_overflow = nullptr;   uint64_t overflow_cap = 0;
+    uint64_t *d_overflow2 = nullptr;  uint64_t overflow2_cap = 0;  // replay target when a replay defers again
     uint64_t *d_dense = nullptr;      // kHistDense bins
     uint64_t *d_big = nullptr;        uint64_t big_cap = 0;
     uint64_t *d_io = nullptr;         uint64_t io_cap = 0;   // generic u64 in/out scratch (device)
@@ -260,6 +271,36 @@ oxg_status grow_to_fit(oxg_table *t, uint64_t keys) {
 
 oxg_status reserve_keys(oxg_table *t, uint64_t extra) { return grow_to_fit(t, t->size + extra); }
 
+// A launch ran into the load limit and deferred `ov` hash OCCURRENCES (not distinct keys: on
+// high-coverage input every new key is deferred many times).  Grow geometrically -- room for
+// at most as many new keys as the table already holds -- and replay; a replay that runs into
+// the limit again defers into the second list and the loop goes round once more.
+oxg_status drain_deferred(oxg_table *t, uint64_t ov) {
+    DeviceCtx *c = t->ctx;
+    if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
+    uint64_t prev = ~0ULL;
+    while (ov) {
+        const uint64_t room = std::min<uint64_t>(ov, std::max<uint64_t>(t->size, 1ull << 20));
+        const uint64_t cap_before = t->cap;
+        TRY(grow_to_fit(t, t->size + room));
+        // deferred for a probe run that would not end rather than for load: double regardless
+        if (t->cap == cap_before && ov >= prev) TRY(grow_to_fit(t, t->cap));
+        prev = ov;
+        TRY(ensure_dev(&c->d_overflow2, &c->overflow2_cap, ov));
+        TRY(zero_ctrl_fields(t, offsetof(Ctrl, overflow) / 8, 1));
+        TableView v = view_of(t, false);
+        v.overflow = c->d_overflow2; v.overflow_cap = c->overflow2_cap;
+        count_hashes_kernel<<<grid_for(c, (ov + 7) / 8, kOpThreads, 8), kOpThreads, 0, c->stream>>>(v, c->d_overflow, ov, nullptr, 0);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        TRY(pull_ctrl(t));
+        ov = t->h_ctrl->overflow;
+        std::swap(c->d_overflow, c->d_overflow2);
+        std::swap(c->overflow_cap, c->overflow2_cap);
+    }
+    return OXG_OK;
+}
+
 // k values with a compile-time specialised consume kernel: klist.h.  Each lives in its own
 // translation unit (consume_inst.cu) and is reached through its entry function.
 #define OXG_DECLARE_ENTRY(KK) extern "C" const void *oxg_consume_entry_##KK(int mode);
@@ -377,14 +418,7 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
             // creating them; the whole-launch count would quadruple the table for nothing),
             // or everything it wanted when it ran into the limit
             t->last_new = (hi - lo) <= kSmallBatch ? 0 : ov ? (t->size - size_before) + ov : 4 * t->h_ctrl->late_new;
-            if (ov) {  // table hit its load limit: grow, then replay the deferred hashes
-                if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
-                TRY(grow_to_fit(t, t->size + ov));
-                count_hashes_kernel<<<grid_for(c, ov, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr, 0);
-                LAUNCHED();
-                CU(cudaGetLastError());
-                TRY(pull_ctrl(t));
-            }
+            if (ov) TRY(drain_deferred(t, ov));  // table hit its load limit: grow, then replay the deferred hashes
         }
         lo = hi;
     }
@@ -649,6 +683,11 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
     // the previous use of buffer b (chunk ci - kStageBufs) is over: its kernels were waited for
     auto issue_copy = [&](uint64_t ci) -> oxg_status {
         const int b = (int)(ci % kStageBufs);
+        // every chunk also validates its share of the offsets (all pairs are seen once per call),
+        // so the O(n_reads) pass runs on the producer thread next to the copies instead of in
+        // front of the first one
+        for (uint64_t r = n_reads * ci / n_chunks, e = n_reads * (ci + 1) / n_chunks; r < e; ++r)
+            if (offsets[r + 1] < offsets[r]) return fail(OXG_ERR_INVALID, "offsets must be non-decreasing");
         const Slice s = slice_of(ci);
         if (c->offs_cap[b] < s.n_off + 1) {
             CU(cudaStreamSynchronize(c->copy));
@@ -687,6 +726,7 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
     uint64_t issued = 0, done = 0;  // chunks whose copies are queued / whose kernels have finished
     bool stop = false;
     oxg_status producer_status = OXG_OK;
+    std::string producer_err;  // g_err is thread-local: carry the producer's message across
     auto produce = [&] {
         cudaSetDevice(c->dev);
         for (uint64_t ci = 0; ci < n_chunks; ++ci) {
@@ -697,7 +737,7 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
             }
             const oxg_status st = issue_copy(ci);
             std::lock_guard<std::mutex> lk(mu);
-            if (st != OXG_OK) { producer_status = st; issued = n_chunks; cv.notify_all(); return; }
+            if (st != OXG_OK) { producer_status = st; producer_err = g_err; issued = n_chunks; cv.notify_all(); return; }
             issued = ci + 1;
             cv.notify_all();
         }
@@ -722,7 +762,7 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
         {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return issued > ci; });
-            if (producer_status != OXG_OK) { st = fail(producer_status, "staging copy failed"); break; }
+            if (producer_status != OXG_OK) { st = fail(producer_status, "%s", producer_err.c_str()); break; }
         }
         st = run_chunk(ci);
         bool found = false;
@@ -759,8 +799,8 @@ oxg_status oxg_consume_batch(oxg_table *t, const uint8_t *bases, const uint64_t 
     if (err_pos) *err_pos = 0;
     if (n_reads == 0) return OXG_OK;
     if (!bases || !offsets) return fail(OXG_ERR_INVALID, "null argument");
-    for (uint64_t r = 0; r < n_reads; ++r)
-        if (offsets[r + 1] < offsets[r]) return fail(OXG_ERR_INVALID, "offsets must be non-decreasing");
+    // (monotonicity of the offsets is checked chunk by chunk while they are staged: stream_span)
+    if (offsets[n_reads] < offsets[0]) return fail(OXG_ERR_INVALID, "offsets must be non-decreasing");
     const uint64_t k = t->k;
     const uint64_t total = offsets[n_reads] - offsets[0];
     const uint64_t n_win = total >= k ? total - k + 1 : 0;
@@ -827,14 +867,7 @@ static oxg_status count_list_device(oxg_table *t, const uint64_t *d_hashes, uint
         t->last_ms += ms; t->last_launches += 1;
         if (counted) *counted += t->h_ctrl->counted;
         const uint64_t ov = t->h_ctrl->overflow;
-        if (ov) {
-            if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
-            TRY(grow_to_fit(t, t->size + ov));
-            count_hashes_kernel<<<grid_for(c, (ov + 7) / 8, kOpThreads, 8), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr, 0);
-            LAUNCHED();
-            CU(cudaGetLastError());
-            TRY(pull_ctrl(t));
-        }
+        if (ov) TRY(drain_deferred(t, ov));
     }
     return OXG_OK;
 }
@@ -1307,14 +1340,7 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
         counted += t->h_ctrl->counted;
         absorbed_total += t->h_ctrl->absorbed;
         const uint64_t ov = t->h_ctrl->overflow;
-        if (ov) {
-            if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
-            TRY(grow_to_fit(t, t->size + ov));
-            count_hashes_kernel<<<grid_for(c, (ov + 7) / 8, kOpThreads, 8), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_overflow, ov, nullptr, 0);
-            LAUNCHED();
-            CU(cudaGetLastError());
-            TRY(pull_ctrl(t));
-        }
+        if (ov) TRY(drain_deferred(t, ov));
         lo = std::max(hi, lo);
         first = false;
     }

@@ -238,7 +238,10 @@ __device__ __forceinline__ void count_fast8(const TableView &tv, const uint64_t 
             const int j = half * 4 + u;
             if (h[j] == 0) continue;  // bad window, or the reference's hash==0 skip (src/lib.rs:589)
             ++n_counted;
-            if (a[u].x == h[j]) red_add64(&tv.slots[idx[u]].y, 1);
+            // the out-of-band key equals the empty-slot marker: it must not "match" an empty
+            // slot; the slow round hands it to table_add, which keeps it in the side entry
+            if (h[j] == kEmpty) pending |= 1u << j;
+            else if (a[u].x == h[j]) red_add64(&tv.slots[idx[u]].y, 1);
             else if (b[u].x == h[j]) red_add64(&tv.slots[idx[u] + 1].y, 1);
             else {
                 pending |= 1u << j;

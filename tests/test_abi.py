@@ -63,3 +63,16 @@ def test_specialised_k_list_is_sane():
     assert {21, 31}.issubset(ks)  # the k values of BASELINE.json's configs; the only ones the route mode is built for
     text = open(os.path.join(_build.CSRC, "capi.cu")).read()
     assert "OXG_FOR_EACH_K(OXG_K_ENTRY)" in text and '#include "klist.h"' in text
+
+
+def test_reference_suite_is_vendored_unmodified():
+    """tests/reference_suite holds the reference's own tests byte for byte (compared here, where
+    /root/reference exists; on the GPU box the comparison has nothing to compare with)."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_suite", "check_unmodified.py")
+    spec = importlib.util.spec_from_file_location("check_unmodified", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main() == 0
