@@ -217,6 +217,17 @@ uint64_t oxg_launch_count(void);
 /* device-time of the consume kernels of the last oxg_consume_* call on `t`, in
  * milliseconds, and their number (CUDA events on the launch stream) */
 oxg_status oxg_last_consume_kernel_ms(oxg_table *t, float *ms, uint64_t *launches);
+/* Process-wide choice of the counting pipeline behind oxg_consume_*: 0 = by launch size
+ * (default: launches of >= 8 Mi windows are partitioned), 1 = always the fused
+ * hash-and-update kernel, 2 = always the partitioned pipeline (hash + scatter, then
+ * aggregate + merge) when the k has a specialised kernel.  n_parts (0 = derived from the
+ * table size; else a power of two in 2..8192) and groups (0 = default) are tuning knobs of
+ * the partitioned pipeline.  Results are identical whichever is chosen.  Initial values come
+ * from OXLI_B200_PIPELINE=fused|part, OXLI_B200_PARTS, OXLI_B200_GROUPS. */
+oxg_status oxg_set_pipeline(int choice, uint32_t n_parts, uint32_t groups);
+/* of that time, the share of the two passes of the partitioned pipeline (hash + scatter,
+ * aggregate + merge); both 0 when the last call ran the fused kernel only */
+oxg_status oxg_last_consume_pass_ms(oxg_table *t, float *ms_scatter, float *ms_aggregate);
 
 #ifdef __cplusplus
 }

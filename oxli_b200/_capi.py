@@ -86,6 +86,8 @@ SIGNATURES = {
     "oxg_timer_stop": (C.c_int, [vp, C.POINTER(C.c_float)]),
     "oxg_launch_count": (u64, []),
     "oxg_last_consume_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float), u64p]),
+    "oxg_set_pipeline": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32]),
+    "oxg_last_consume_pass_ms": (C.c_int, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
 }
 
 
@@ -292,6 +294,11 @@ class Table:
         check(lib.oxg_last_consume_kernel_ms(self._h, C.byref(ms), C.byref(n)))
         return float(ms.value), int(n.value)
 
+    def last_consume_pass_ms(self) -> tuple[float, float]:
+        a, b = C.c_float(), C.c_float()
+        check(lib.oxg_last_consume_pass_ms(self._h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
     def digest(self) -> dict:
         """Order-independent digests of the (hash, count) multiset (test helper)."""
         k, v = self.export(1)
@@ -302,6 +309,12 @@ class Table:
                 "xor": int(np.bitwise_xor.reduce(k)) if len(k) else 0,
                 "sum_hc": int((k * v).sum(dtype=np.uint64)),
             }
+
+
+def set_pipeline(choice: int | str = 0, n_parts: int = 0, groups: int = 0) -> None:
+    """0/'auto', 1/'fused', 2/'part' (see oxg_set_pipeline)."""
+    choice = {"auto": 0, "fused": 1, "part": 2}.get(choice, choice)
+    check(lib.oxg_set_pipeline(int(choice), n_parts, groups))
 
 
 def device_alloc(nbytes: int, device: int = 0) -> int:

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/oxli_b200.h"
+#include "aggregate.cuh"
 #include "consume.cuh"
 #include "klist.h"
 #include "tableops.cuh"
@@ -71,6 +72,18 @@ static const uint64_t kChunkBytes = [] {
 constexpr uint64_t kLaunchWindows = 64ull << 20;  // windows per consume launch (bounds the overflow list)
 constexpr uint64_t kSmallBatch = 1ull << 20;      // below this, reserve for the worst case up front
 constexpr uint64_t kMinCap = 1024;
+// Launches of at least this many windows go through the partitioned pipeline (pass A scatter,
+// pass B aggregate + merge); smaller ones keep the fused kernel, whose fixed costs are lower.
+// OXLI_B200_PIPELINE=fused|part overrides the choice (part still needs a specialised k).
+constexpr uint64_t kPartMinWindows = 8ull << 20;
+static int env_int(const char *name, int dflt) { const char *e = getenv(name); return e && *e ? atoi(e) : dflt; }
+// 0 = by launch size, 1 = fused kernel only, 2 = partitioned whenever the k is specialised
+static std::atomic<int> g_pipeline{[] {
+    const char *e = getenv("OXLI_B200_PIPELINE");
+    return e && !strcmp(e, "fused") ? 1 : e && !strcmp(e, "part") ? 2 : 0;
+}()};
+static std::atomic<uint32_t> g_parts_override{(uint32_t)env_int("OXLI_B200_PARTS", 0)};    // 0 = from the table size
+static std::atomic<uint32_t> g_groups_override{(uint32_t)env_int("OXLI_B200_GROUPS", 0)};  // 0 = default
 constexpr int kStageBufs = 4;  // host batches: chunks in flight between the copy stream and the kernels
 
 struct DeviceCtx {
@@ -86,18 +99,24 @@ struct DeviceCtx {
     uint64_t *h_offs[kStageBufs] = {};
     uint64_t offs_cap[kStageBufs] = {};
     cudaEvent_t ev_ready[kStageBufs] = {};
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_mid = nullptr;
     cudaEvent_t ev_user0 = nullptr, ev_user1 = nullptr;
     // scratch
     uint64_t *d_tile_first = nullptr; uint64_t tile_first_cap = 0;
-    uint64_t *d_overflow = nullptr;   uint64_t overflow_cap = 0;
-    uint64_t *d_overflow2 = nullptr;  uint64_t overflow2_cap = 0;  // replay target when a replay defers again
+    ulonglong2 *d_overflow = nullptr;   uint64_t overflow_cap = 0;   // deferred (key, increment) pairs
+    ulonglong2 *d_overflow2 = nullptr;  uint64_t overflow2_cap = 0;  // replay target when a replay defers again
     uint64_t *d_dense = nullptr;      // kHistDense bins
     uint64_t *d_big = nullptr;        uint64_t big_cap = 0;
     uint64_t *d_io = nullptr;         uint64_t io_cap = 0;   // generic u64 in/out scratch (device)
     uint64_t *h_io = nullptr;         uint64_t h_io_cap = 0; // pinned mirror
     double *d_f64 = nullptr;          // 4 doubles
     uint8_t *d_seq = nullptr;         uint64_t seq_cap = 0;  // hash_windows input
+    // partitioned pipeline (pass A output): fragments, their fill counts, the spill list
+    uint64_t *d_frag = nullptr;       uint64_t frag_cap = 0;
+    uint32_t *d_frag_cnt = nullptr;   uint64_t frag_cnt_cap = 0;
+    uint64_t *d_spill = nullptr;      uint64_t spill_cap = 0;
+    unsigned long long *d_spill_n = nullptr;
+    bool agg_attr_done = false;
 };
 
 std::mutex g_ctx_mu;
@@ -127,6 +146,7 @@ oxg_status get_ctx(int dev, DeviceCtx **out) {
         for (int i = 0; i < kStageBufs; ++i) CU(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
         CU(cudaEventCreate(&c->ev_t0));
         CU(cudaEventCreate(&c->ev_t1));
+        CU(cudaEventCreate(&c->ev_mid));
         CU(cudaEventCreate(&c->ev_user0));
         CU(cudaEventCreate(&c->ev_user1));
         CU(cudaMalloc(&c->d_dense, kHistDense * sizeof(uint64_t)));
@@ -201,6 +221,8 @@ struct oxg_table {
     Ctrl *h_ctrl = nullptr;  // pinned
     uint64_t size = 0;       // host mirror of ctrl->size as of the last sync
     bool hinted = false;     // the caller said how many distinct keys to expect
+    uint64_t hint_keys = 0;  // ... and this many
+    float last_ms_a = 0.f, last_ms_b = 0.f;  // partitioned pipeline: pass A / pass B share of last_ms
     uint64_t last_new = 0;   // keys created by the previous consume launch (growth look-ahead)
     float last_ms = 0.f;
     uint64_t last_launches = 0;
@@ -290,7 +312,7 @@ oxg_status drain_deferred(oxg_table *t, uint64_t ov) {
         TRY(zero_ctrl_fields(t, offsetof(Ctrl, overflow) / 8, 1));
         TableView v = view_of(t, false);
         v.overflow = c->d_overflow2; v.overflow_cap = c->overflow2_cap;
-        count_hashes_kernel<<<grid_for(c, (ov + 7) / 8, kOpThreads, 8), kOpThreads, 0, c->stream>>>(v, c->d_overflow, ov, nullptr, 0);
+        replay_pairs_kernel<<<grid_for(c, (ov + 3) / 4, kOpThreads, 8), kOpThreads, 0, c->stream>>>(v, c->d_overflow, ov);
         LAUNCHED();
         CU(cudaGetLastError());
         TRY(pull_ctrl(t));
@@ -356,6 +378,119 @@ oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
     return OXG_OK;
 }
 
+
+// ---- partitioned pipeline: pass A (hash + scatter) and pass B (aggregate + merge) -----------
+
+struct PartPlan {
+    uint32_t n_parts = 0, part_bits = 0;   // partitions of one rank's table
+    int n_ranks = 1, self_rank = 0, owner_shift = 64;
+    uint32_t grid_a = 0;                   // CTAs of pass A = fragments per destination
+    uint32_t frag_cap = 0;                 // entries per fragment
+    uint64_t spill_cap = 0;
+    uint32_t groups = 1;
+    uint32_t n_dest() const { return n_parts * (uint32_t)n_ranks; }
+    uint64_t frag_entries() const { return (uint64_t)n_dest() * grid_a * frag_cap; }
+};
+
+bool use_partitioned(const oxg_table *t, uint64_t span) {
+    if (!specialised_entry(t->k, kModePart)) return false;
+    const int choice = g_pipeline.load();
+    if (choice == 1) return false;
+    if (choice == 2) return true;
+    return span >= kPartMinWindows;
+}
+
+// Partition count: about 2048 distinct keys per partition, so that the shared-memory table of
+// pass B (8192 slots) holds a partition's keys at load <= 0.3 and duplicates meet there.
+uint32_t choose_parts(const oxg_table *t) {
+    const uint32_t forced = g_parts_override.load();
+    if (forced >= 2 && forced <= 8192 && !(forced & (forced - 1))) return forced;
+    const uint64_t est = std::max(t->size + t->last_new, t->hint_keys);
+    if (est == 0) return 1024;
+    uint64_t parts = 64;
+    while (parts < 4096 && parts * 2048 < est) parts <<= 1;
+    return (uint32_t)parts;
+}
+
+oxg_status plan_partitioned(oxg_table *t, uint64_t span, uint64_t n_tiles, int n_ranks, int self_rank, PartPlan *out) {
+    DeviceCtx *c = t->ctx;
+    PartPlan pl;
+    pl.n_parts = choose_parts(t);
+    while ((1u << pl.part_bits) < pl.n_parts) ++pl.part_bits;
+    pl.n_ranks = n_ranks; pl.self_rank = self_rank;
+    int lg = 0;
+    while ((1 << lg) < n_ranks) ++lg;
+    pl.owner_shift = 64 - lg;
+    const void *fn = specialised_entry(t->k, kModePart);
+    const size_t dyn = consume_dyn_smem(kModePart, pl.n_dest());
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, dyn) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const uint64_t tiles_per_cta = kThreads / 32;
+    pl.grid_a = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n_tiles + tiles_per_cta - 1) / tiles_per_cta, (uint64_t)c->sms * per_sm));
+    // a fragment holds its fair share of the launch's windows plus half again plus a few sectors;
+    // what does not fit (skew) goes to the spill list, which can take the whole launch
+    const uint64_t fair = span / ((uint64_t)pl.n_dest() * pl.grid_a) + 1;
+    pl.frag_cap = (uint32_t)((fair + fair / 2 + 24 + 3) & ~3ull);
+    pl.spill_cap = span;
+    const uint32_t forced_groups = g_groups_override.load();
+    pl.groups = forced_groups ? forced_groups : 1;
+    if (pl.frag_entries() >> 32) return fail(OXG_ERR_INVALID, "internal: fragment buffer too large for one launch");
+    *out = pl;
+    return OXG_OK;
+}
+
+oxg_status ensure_part_buffers(DeviceCtx *c, const PartPlan &pl) {
+    TRY(ensure_dev(&c->d_frag, &c->frag_cap, pl.frag_entries()));
+    TRY(ensure_dev(&c->d_frag_cnt, &c->frag_cnt_cap, (uint64_t)pl.n_dest() * pl.grid_a));
+    TRY(ensure_dev(&c->d_spill, &c->spill_cap, pl.spill_cap));
+    if (!c->d_spill_n) CU(cudaMalloc(&c->d_spill_n, 8));
+    return OXG_OK;
+}
+
+// pass A: p is a filled-in ConsumeParams (table.ctrl is where `counted` goes)
+oxg_status launch_part_a(oxg_table *t, ConsumeParams p, const PartPlan &pl, uint64_t *d_frag, uint32_t *d_frag_cnt,
+                         uint64_t *d_spill, unsigned long long *d_spill_n) {
+    DeviceCtx *c = t->ctx;
+    const void *fn = specialised_entry(t->k, kModePart);
+    const size_t dyn = consume_dyn_smem(kModePart, pl.n_dest());
+    p.frag = d_frag; p.frag_cnt = d_frag_cnt; p.frag_cap = pl.frag_cap;
+    p.n_parts = pl.n_parts; p.part_shift = 64 - pl.part_bits; p.n_dest = pl.n_dest();
+    p.n_ranks = pl.n_ranks; p.self_rank = pl.self_rank; p.owner_shift = pl.owner_shift;
+    p.spill = d_spill; p.spill_cap = pl.spill_cap; p.spill_n = d_spill_n;
+    CU(cudaMemsetAsync(d_spill_n, 0, 8, c->stream));
+    void *args[] = {&p};
+    CU(cudaLaunchKernel(fn, dim3(pl.grid_a), dim3(kThreads), args, dyn, c->stream));
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return OXG_OK;
+}
+
+// pass B over n_src sources (one, this device's own pass A output, without sharding)
+oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src, int n_src) {
+    DeviceCtx *c = t->ctx;
+    const size_t smem = aggregate_smem_bytes();
+    if (!c->agg_attr_done) {
+        CU(cudaFuncSetAttribute((const void *)aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->agg_attr_done = true;
+    }
+    AggParams a{};
+    a.table = view_of(t, true);
+    for (int s = 0; s < n_src; ++s) a.src[s] = src[s];
+    a.n_src = n_src;
+    a.n_parts = pl.n_parts; a.dest0 = (uint32_t)pl.self_rank * pl.n_parts; a.n_ctas = pl.grid_a;
+    a.frag_cap = pl.frag_cap; a.part_bits = pl.part_bits; a.groups = pl.groups; a.spill_cap = pl.spill_cap;
+    a.owner_shift = pl.owner_shift; a.self_rank = pl.self_rank; a.n_ranks = pl.n_ranks;
+    a.work_counter = (unsigned long long *)&t->d_ctrl->absorb_counter;
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)aggregate_kernel, kAggThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const uint64_t items = (uint64_t)pl.n_parts * pl.groups;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(items, (uint64_t)c->sms * per_sm));
+    aggregate_kernel<<<grid, kAggThreads, smem, c->stream>>>(a);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    return OXG_OK;
+}
+
 // Run one mode over window starts [w_lo, w_hi) of a device-resident span.
 // `bases` holds global positions [g0, data_end); offsets are global positions.
 // kModeCount: loops launches of <= kLaunchWindows windows, growing the table and
@@ -400,8 +535,19 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
         tile_first_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(d_offsets, n_off, tile_base, n_tiles, tw, c->d_tile_first);
         LAUNCHED();
         CU(cudaGetLastError());
+        const bool part = mode == kModeCount && use_partitioned(t, hi - lo);
+        PartPlan pl;
+        if (part) {
+            TRY(plan_partitioned(t, hi - lo, n_tiles, 1, 0, &pl));
+            TRY(ensure_part_buffers(c, pl));
+        }
         CU(cudaEventRecord(c->ev_t0, c->stream));
-        if (mode == kModeCount) TRY(launch_consume<kModeCount>(t, p));
+        if (part) {
+            TRY(launch_part_a(t, p, pl, c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n));
+            CU(cudaEventRecord(c->ev_mid, c->stream));
+            const AggSource own{c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n};
+            TRY(launch_part_b(t, pl, &own, 1));
+        } else if (mode == kModeCount) TRY(launch_consume<kModeCount>(t, p));
         else if (mode == kModeHash) TRY(launch_consume<kModeHash>(t, p));
         else TRY(launch_consume<kModeFirstBad>(t, p));
         CU(cudaEventRecord(c->ev_t1, c->stream));
@@ -411,6 +557,14 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
             float ms = 0.f;
             CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
             t->last_ms += ms; t->last_launches += 1;
+            if (part) {
+                float ms_a = 0.f;
+                CU(cudaEventElapsedTime(&ms_a, c->ev_t0, c->ev_mid));
+                t->last_ms_a += ms_a; t->last_ms_b += ms - ms_a;
+                // no look-ahead counter here: what this launch created is the forecast for the
+                // next one, unless the caller's hint still covers the table
+                t->h_ctrl->late_new = (t->hinted && t->size <= t->hint_keys) ? 0 : (t->size - size_before) / 4;
+            }
             if (counted) *counted += t->h_ctrl->counted;
             uint64_t ov = t->h_ctrl->overflow;
             // what the next launch of this stream will probably create: the rate of the last
@@ -435,7 +589,7 @@ oxg_status consume_resident(oxg_table *t, const uint8_t *d_bases, const uint64_t
     uint64_t counted = 0;
     if (err_read) *err_read = -1;
     if (err_pos) *err_pos = 0;
-    t->last_ms = 0.f; t->last_launches = 0;
+    t->last_ms = 0.f; t->last_ms_a = 0.f; t->last_ms_b = 0.f; t->last_launches = 0;
     const uint64_t n_win = total >= k ? total - k + 1 : 0;
     oxg_status ret = OXG_OK;
     if (skip_bad || n_win == 0) {
@@ -500,6 +654,7 @@ oxg_status oxg_table_create(int device, uint32_t ksize, uint64_t capacity_hint, 
     t->ctx = c; t->k = ksize;
     t->cap = capacity_for_keys(capacity_hint);
     t->hinted = capacity_hint != 0;
+    t->hint_keys = capacity_hint;
     CU(cudaMalloc(&t->d_ctrl, sizeof(Ctrl)));
     CU(cudaMemsetAsync(t->d_ctrl, 0, sizeof(Ctrl), c->stream));
     CU(cudaMallocHost(&t->h_ctrl, sizeof(Ctrl)));
@@ -581,6 +736,23 @@ oxg_status oxg_last_consume_kernel_ms(oxg_table *t, float *ms, uint64_t *launche
     if (!t) return fail(OXG_ERR_INVALID, "table is null");
     if (ms) *ms = t->last_ms;
     if (launches) *launches = t->last_launches;
+    return OXG_OK;
+}
+
+oxg_status oxg_set_pipeline(int choice, uint32_t n_parts, uint32_t groups) {
+    if (choice < 0 || choice > 2) return fail(OXG_ERR_INVALID, "pipeline choice must be 0 (by size), 1 (fused) or 2 (partitioned)");
+    if (n_parts && (n_parts < 2 || n_parts > 8192 || (n_parts & (n_parts - 1))))
+        return fail(OXG_ERR_INVALID, "n_parts must be 0 or a power of two in 2..8192");
+    g_pipeline.store(choice);
+    g_parts_override.store(n_parts);
+    g_groups_override.store(groups);
+    return OXG_OK;
+}
+
+oxg_status oxg_last_consume_pass_ms(oxg_table *t, float *ms_scatter, float *ms_aggregate) {
+    if (!t) return fail(OXG_ERR_INVALID, "table is null");
+    if (ms_scatter) *ms_scatter = t->last_ms_a;
+    if (ms_aggregate) *ms_aggregate = t->last_ms_b;
     return OXG_OK;
 }
 
@@ -804,7 +976,7 @@ oxg_status oxg_consume_batch(oxg_table *t, const uint8_t *bases, const uint64_t 
     const uint64_t k = t->k;
     const uint64_t total = offsets[n_reads] - offsets[0];
     const uint64_t n_win = total >= k ? total - k + 1 : 0;
-    t->last_ms = 0.f; t->last_launches = 0;
+    t->last_ms = 0.f; t->last_ms_a = 0.f; t->last_ms_b = 0.f; t->last_launches = 0;
     if (n_win == 0) return OXG_OK;
     cudaPointerAttributes attr{};
     bool pinned = cudaPointerGetAttributes(&attr, bases) == cudaSuccess && attr.type == cudaMemoryTypeHost;
@@ -877,7 +1049,7 @@ oxg_status oxg_count_hashes_device(oxg_table *t, const uint64_t *d_hashes, uint6
     if (n_counted) *n_counted = 0;
     if (n == 0) return OXG_OK;
     if (!d_hashes) return fail(OXG_ERR_INVALID, "null argument");
-    t->last_ms = 0.f; t->last_launches = 0;
+    t->last_ms = 0.f; t->last_ms_a = 0.f; t->last_ms_b = 0.f; t->last_launches = 0;
     return count_list_device(t, d_hashes, n, skip_zero, n_counted);
 }
 
@@ -1288,7 +1460,7 @@ oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const ui
     if (absorbed) *absorbed = 0;
     const uint64_t k = t->k;
     CU(cudaMemsetAsync(d_out_counts, 0, (size_t)n_ranks * 8, c->stream));
-    t->last_ms = 0.f; t->last_launches = 0;
+    t->last_ms = 0.f; t->last_ms_a = 0.f; t->last_ms_b = 0.f; t->last_launches = 0;
     uint64_t counted = 0, absorbed_total = 0;
     const uint64_t w_end = base_hi - base_lo >= k ? base_hi - k + 1 : base_lo;  // one past the last window start
     int lg = 0;

@@ -50,7 +50,8 @@ enum Mode : int {
     kModeCount = 0,    // hash + count into the table
     kModeHash = 1,     // hash only, write one u64 per window (0 = bad window)
     kModeFirstBad = 2, // error-mode pre-scan: smallest in-read window holding a bad byte
-    kModeRoute = 3     // multi-GPU: count hashes owned by this rank, append the rest per owner
+    kModeRoute = 3,    // multi-GPU: count hashes owned by this rank, append the rest per owner
+    kModePart = 4      // hash + scatter into per-CTA fragments, one per table partition (pass A)
 };
 
 struct ConsumeParams {
@@ -80,6 +81,21 @@ struct ConsumeParams {
     uint64_t absorb_n[kMaxRanks];
     uint64_t absorb_first[kMaxRanks + 1];
     int n_absorb;
+    // kModePart (pass A of the partitioned pipeline, see aggregate.cuh).  Destination of hash h:
+    //   dest = owner(h) * n_parts + ((h * phi) >> part_shift)      owner(h) = h >> owner_shift, 0 with one rank
+    // so a destination is (rank, contiguous segment of that rank's table).  Every CTA owns one
+    // fragment of frag_cap entries per destination: frag[(dest * gridDim.x + blockIdx.x) * frag_cap ..];
+    // a hash whose fragment is full goes to the spill list.  frag_cnt[dest * gridDim.x + blockIdx.x]
+    // = entries written.
+    uint64_t *frag;
+    uint32_t *frag_cnt;
+    uint32_t frag_cap;
+    uint32_t n_parts;        // partitions per rank (power of two, >= 2)
+    uint32_t part_shift;     // 64 - log2(n_parts)
+    uint32_t n_dest;         // n_ranks * n_parts
+    uint64_t *spill;
+    uint64_t spill_cap;
+    unsigned long long *spill_n;
 };
 
 static __global__ void tile_first_kernel(const uint64_t *__restrict__ offsets, uint64_t n_off,
@@ -342,6 +358,12 @@ __global__ void __launch_bounds__(kThreads, (MODE == kModeRoute || K > 32) ? 2 :
 
     uint64_t n_absorbed = 0;
     uint8_t *dyn = dyn_smem + (kCounts ? warp * kDynPerWarp : 0);
+    // pass A: one fill counter per destination, shared by the CTA's warps, alive for the whole launch
+    uint32_t *s_fill = reinterpret_cast<uint32_t *>(dyn_smem);
+    if (MODE == kModePart) {
+        for (uint32_t i = threadIdx.x; i < p.n_dest; i += kThreads) s_fill[i] = 0;
+        __syncthreads();
+    }
     SlowQueue queue{reinterpret_cast<uint64_t *>(dyn), dyn + kQueueCap * 8, 0};
     uint32_t created = 0;
     bool late = false;  // working on the last quarter of the launch's tiles
@@ -576,7 +598,40 @@ __global__ void __launch_bounds__(kThreads, (MODE == kModeRoute || K > 32) ? 2 :
             if (t_nxt < p.n_tiles) prefetch_offsets(tf_next, s_off_all[warp][buf ^ 1]);
             cp_async_commit();
 
-            if (MODE == kModeHash) {
+            if (MODE == kModePart) {
+                // One shared-memory atomic hands out the position inside this CTA's fragment of the
+                // destination; the store goes straight to it.  No global atomics, no barrier: the
+                // 8-byte stores of a fragment's sector meet in L2 before they reach DRAM.
+                uint32_t spilled = 0;
+                const uint64_t frag_row = (uint64_t)gridDim.x * p.frag_cap;
+                uint64_t *const my_frag = p.frag + (uint64_t)blockIdx.x * p.frag_cap;
+#pragma unroll
+                for (int j = 0; j < kWPT; ++j) {
+                    if (h[j] == 0) continue;
+                    ++n_counted;
+                    uint32_t dest = (uint32_t)((h[j] * kPhi) >> p.part_shift);
+                    if (p.n_ranks > 1) dest += (uint32_t)(h[j] >> p.owner_shift) * p.n_parts;
+                    const uint32_t pos = atomicAdd(&s_fill[dest], 1u);
+                    if (pos < p.frag_cap) my_frag[dest * frag_row + pos] = h[j];
+                    else spilled |= 1u << j;
+                }
+                if (__any_sync(0xffffffffu, spilled != 0)) {
+                    // skewed input (one k-mer flooding its partition): one reservation per warp tile
+                    const uint32_t mine = __popc(spilled);
+                    uint32_t incl = mine;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(p.spill_n, (unsigned long long)total);
+                    base = __shfl_sync(0xffffffffu, base, 0) + (incl - mine);
+#pragma unroll
+                    for (int j = 0; j < kWPT; ++j)
+                        if ((spilled >> j) & 1u) { if (base < p.spill_cap) p.spill[base] = h[j]; ++base; }
+                }
+            } else if (MODE == kModeHash) {
 #pragma unroll
                 for (int j = 0; j < kWPT; ++j)
                     if (gp0 + j >= p.w_lo && gp0 + j < p.w_hi) p.hashes_out[gp0 + j - p.w_lo] = h[j];
@@ -650,11 +705,16 @@ __global__ void __launch_bounds__(kThreads, (MODE == kModeRoute || K > 32) ? 2 :
         while (queue.n) slow_round(p.table, queue, __ldcg(&p.table.ctrl->size) >= p.table.limit, created);
         flush_created();
     }
+    if (MODE == kModePart) {
+        __syncthreads();  // every warp of the CTA is done scattering
+        for (uint32_t i = threadIdx.x; i < p.n_dest; i += kThreads)
+            p.frag_cnt[(uint64_t)i * gridDim.x + blockIdx.x] = min(s_fill[i], p.frag_cap);
+    }
     if (MODE == kModeFirstBad) {
         for (int o = 16; o; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
         if (lane == 0 && first_bad != ~0ULL)
             atomicMin((unsigned long long *)&p.table.ctrl->first_bad, (unsigned long long)first_bad);
-    } else if (kCounts) {
+    } else if (kCounts || MODE == kModePart) {
         for (int o = 16; o; o >>= 1) n_counted += __shfl_xor_sync(0xffffffffu, n_counted, o);
         if (lane == 0 && n_counted)
             atomicAdd((unsigned long long *)&p.table.ctrl->counted, (unsigned long long)n_counted);
@@ -785,7 +845,8 @@ inline size_t generic_smem_bytes(int k) {
 
 namespace oxg {
 // dynamic shared memory a specialised consume launch needs
-inline size_t consume_dyn_smem(int mode) {
+inline size_t consume_dyn_smem(int mode, uint32_t n_dest = 0) {
+    if (mode == kModePart) return (size_t)n_dest * 4;
     if (mode != kModeCount && mode != kModeRoute) return 0;
     return (size_t)(kThreads / 32) * (kQueueCap * 9 + (mode == kModeRoute ? kWarpTile * 8 : 0));
 }

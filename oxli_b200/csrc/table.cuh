@@ -48,7 +48,7 @@ struct TableView {
     uint32_t shift;    // 64 - log2(cap)
     uint64_t limit;    // stop creating keys once size reaches this
     Ctrl *ctrl;
-    uint64_t *overflow;   // deferred hashes (table too full), may be null
+    ulonglong2 *overflow;  // deferred (key, increment) pairs (table too full), may be null
     uint64_t overflow_cap;
     // home slot: even, so a key's first two candidate slots share one 32-byte sector
     __device__ __forceinline__ uint64_t home(uint64_t key) const {
@@ -69,17 +69,17 @@ __device__ __forceinline__ void load_pair(const ulonglong2 *p, ulonglong2 &a, ul
         : "l"(p));
 }
 
-// Deferred hashes go to one list with one cursor: the lanes that arrive together reserve
-// their entries with a single atomic (a launch that fills the table defers tens of
-// millions of hashes; one atomic each on one address cost 7x the kernel time).
-__device__ __forceinline__ void push_overflow(const TableView &t, uint64_t key) {
+// Deferred updates go to one list of (key, increment) pairs with one cursor: the lanes that
+// arrive together reserve their entries with a single atomic (a launch that fills the table
+// defers tens of millions of hashes; one atomic each on one address cost 7x the kernel time).
+__device__ __forceinline__ void push_overflow(const TableView &t, uint64_t key, uint64_t inc) {
     const unsigned peers = __activemask();
     const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
     unsigned long long base = 0;
     if (lane == leader) base = atomicAdd((unsigned long long *)&t.ctrl->overflow, (unsigned long long)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     const uint64_t at = base + __popc(peers & ((1u << lane) - 1));
-    if (t.overflow && at < t.overflow_cap) t.overflow[at] = key;
+    if (t.overflow && at < t.overflow_cap) t.overflow[at] = make_ulonglong2(key, inc);
 }
 
 // counts[key] += inc.  `full` = do not create keys (the table reached its load
@@ -114,7 +114,7 @@ __device__ __forceinline__ uint32_t table_add(const TableView &t, uint64_t key, 
         }
         i = (i + 1) & (t.cap - 1);
     }
-    push_overflow(t, key);
+    push_overflow(t, key, inc);
     return 0;
 }
 
@@ -134,7 +134,7 @@ __device__ __forceinline__ uint32_t table_add_buckets(const TableView &t, uint64
                 return 0;
             }
             if (s[q].x == kEmpty) {
-                if (full) { push_overflow(t, key); return 0; }
+                if (full) { push_overflow(t, key, inc); return 0; }
                 const uint64_t old = atomicCAS((unsigned long long *)&t.slots[i + q].x, kEmpty, key);
                 if (old == kEmpty || old == key) {
                     red_add64(&t.slots[i + q].y, inc);
@@ -144,8 +144,36 @@ __device__ __forceinline__ uint32_t table_add_buckets(const TableView &t, uint64
         }
         i = (i + 2) & (t.cap - 1);
     }
-    push_overflow(t, key);
+    push_overflow(t, key, inc);
     return 0;
+}
+
+// counts[key[u]] += inc[u] for the lanes' U live entries, all home buckets requested before the
+// first is examined (one dependent random sector per update is what bounds this; see
+// table_get_many).  Returns the number of keys created.
+template <int U>
+__device__ __forceinline__ uint32_t table_add_many(const TableView &t, const uint64_t (&key)[U], const uint64_t (&inc)[U],
+                                                   uint32_t live, bool full) {
+    uint64_t idx[U];
+    ulonglong2 a[U], b[U];
+    uint32_t created = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (((live >> u) & 1u) && key[u] == kEmpty) { created += table_add(t, key[u], inc[u], full); live &= ~(1u << u); }
+        idx[u] = t.home(key[u]);
+        if ((live >> u) & 1u) load_pair(t.slots + idx[u], a[u], b[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (!((live >> u) & 1u)) continue;
+        if (a[u].x == key[u]) red_add64(&t.slots[idx[u]].y, inc[u]);
+        else if (b[u].x == key[u]) red_add64(&t.slots[idx[u] + 1].y, inc[u]);
+        else {
+            const bool redo = a[u].x == kEmpty || b[u].x == kEmpty;
+            created += table_add_buckets(t, key[u], inc[u], full, (idx[u] + (redo ? 0 : 2)) & (t.cap - 1));
+        }
+    }
+    return created;
 }
 
 // same, but returns the count after the increment (count_hash, src/lib.rs:100-104);

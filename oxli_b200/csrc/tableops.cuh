@@ -77,6 +77,29 @@ __global__ void __launch_bounds__(kOpThreads) count_hashes_kernel(TableView t, c
     }
 }
 
+// Replay of a deferral list: counts[key] += inc for (key, inc) pairs, four in flight per thread;
+// at the load limit again, pairs go on to the view's own deferral list.
+__global__ void __launch_bounds__(kOpThreads) replay_pairs_kernel(TableView t, const ulonglong2 *__restrict__ pairs, uint64_t n) {
+    constexpr int U = 4;
+    uint32_t created = 0;
+    const uint64_t stride = gstride();
+    for (uint64_t base = gtid(); base < n; base += stride * U) {
+        const bool full = t.overflow != nullptr && __ldcg(&t.ctrl->size) >= t.limit;
+        uint64_t key[U], inc[U];
+        uint32_t live = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t i = base + u * stride;
+            const ulonglong2 e = i < n ? pairs[i] : make_ulonglong2(0, 0);
+            key[u] = e.x; inc[u] = e.y;
+            live |= (i < n ? 1u : 0u) << u;
+        }
+        created += table_add_many<U>(t, key, inc, live, full);
+    }
+    const uint64_t tot = warp_sum(created);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd((unsigned long long *)&t.ctrl->size, (unsigned long long)tot);
+}
+
 // counts[key] += val for (key,val) pairs; creates keys (also with val == 0)
 __global__ void add_pairs_kernel(TableView t, const uint64_t *__restrict__ keys, const uint64_t *__restrict__ vals, uint64_t n) {
     uint32_t created = 0;
