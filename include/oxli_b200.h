@@ -135,6 +135,11 @@ oxg_status oxg_table_stats(oxg_table *t, oxg_stats *out);
  * pairs; call with cap = 0 to size the buffers. */
 oxg_status oxg_histo(oxg_table *t, uint64_t *freq, uint64_t *n, uint64_t cap, uint64_t *n_out);
 
+/* order-independent digests of this table (parity checks at sizes where nothing can be
+ * exported): out = {len, sum c, xor h, sum h*c mod 2^64, keys whose owner
+ * h >> (64 - log2 n_ranks) is not `rank`}; n_ranks = 1, rank = 0 for a plain table */
+oxg_status oxg_table_digest(oxg_table *t, int n_ranks, int rank, uint64_t out[5]);
+
 /* ---- export: hashes / dump / __iter__ (src/lib.rs:330-381, 517-521, 658) ---
  * sort_mode 0: table (slot) order -- stable between calls while the table is
  * not modified, so dump() == list(iter); 1: by key; 2: by (count, key). */
@@ -160,36 +165,78 @@ oxg_status oxg_cosine(oxg_table *a, oxg_table *b, double *out);
 /* ---- merge: KmerCountTable::add (src/lib.rs:778-837) ---------------------- */
 oxg_status oxg_merge(oxg_table *dst, oxg_table *src, uint64_t *counts_added, uint64_t *new_keys);
 
-/* ---- multi-GPU building blocks (table sharded by the high bits of the hash;
- * one process per GPU) -------------------------------------------------------
- * Hash the reads covering bytes [base_lo, base_hi) of a device-resident batch
- * (both must be read boundaries; d_offsets is the whole batch's CSR array).
- * Hashes owned by `self_rank` (owner(h) = h >> (64 - log2 n_ranks)) are counted
- * into `t` directly; the others are appended to d_out[owner] (capacity out_cap
- * entries each) -- d_out[] may point into PEER memory (oxg_ipc_import), in which
- * case the kernel's stores are the exchange.  d_out_counts (n_ranks entries,
- * device) receives the number appended per destination and is copied to
- * out_counts (host).  The same launch also absorbs hashes that other ranks
- * routed here earlier: n_absorb device segments d_absorb[i] of absorb_n[i]
- * hashes (host arrays; n_absorb may be 0).  *local_counted = k-mers of this
- * rank's reads counted locally, *absorbed = received hashes counted.
- * n_ranks: power of two, 2..16; k = 21 or 31. */
-oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const uint64_t *d_offsets,
-                                  uint64_t n_reads, uint64_t base_lo, uint64_t base_hi, int n_ranks,
-                                  int self_rank, uint64_t *const *d_out, uint64_t out_cap,
-                                  uint64_t *d_out_counts, uint64_t *out_counts,
-                                  uint64_t *local_counted, int n_absorb,
-                                  const uint64_t *const *d_absorb, const uint64_t *absorb_n,
-                                  uint64_t *absorbed);
-
-/* Peer memory for the fused exchange: a rank exports the receive buffer it
- * allocated with oxg_device_alloc, its peers (other processes, one per GPU of the
- * same node) import it and pass pointers into it as d_out[] of
- * oxg_route_batch_device, so the route kernel stores remote hashes straight into
- * the owner's HBM over NVLink.  handle = 64 bytes (cudaIpcMemHandle_t). */
-oxg_status oxg_ipc_export(int device, void *d_ptr, uint8_t handle_out[64]);
-oxg_status oxg_ipc_import(int device, const uint8_t handle[64], void **d_ptr_out);
-oxg_status oxg_ipc_close(int device, void *d_ptr);
+/* ---- hash-sharded table across the GPUs of one node ------------------------
+ * The north_star's multi-GPU layout: shard r of N owns the hashes with
+ * h >> (64 - log2 N) == r; the reference's primitive for combining partial
+ * tables is KmerCountTable::add (src/lib.rs:778-837), here replaced by routing
+ * every hash to its owner before it is counted.  One oxg_shard per GPU.  The
+ * shards of a table live in one process each (the usual arrangement, connected
+ * through CUDA IPC handles that the launcher passes around) or in one process
+ * together (oxg_shard_connect_local; also how a single-GPU box tests N > 1).
+ *
+ * Exchange: every rank hashes ITS reads and leaves the hashes in its own HBM,
+ * in fragments addressed by (owner, table partition); the owner's aggregation
+ * kernel reads the fragments of all ranks through peer-mapped pointers, so the
+ * NVLink transfer is that kernel's load stream.  Ranks synchronise through
+ * 8-byte flags in each other's exchange header, awaited on the GPU: no host
+ * round trip per round, no collective library.
+ *
+ * oxg_shard_consume_batch* is COLLECTIVE: every rank of the table calls it (with
+ * its own reads, possibly none), as are the oxg_shard_* reductions below.  A
+ * shard handle is used by one thread at a time; different shards of one process
+ * are driven by different threads.  n_ranks: power of two, 1..16; the k must have
+ * a specialised kernel (csrc/klist.h).  capacity_hint = distinct keys expected in
+ * THIS shard (0 = unknown); round_windows = window starts per exchange round
+ * (0 = 64 Mi), which fixes the size of the exchange area -- all ranks must pass
+ * the same ksize, n_ranks, capacity_hint and round_windows. */
+typedef struct oxg_shard oxg_shard;
+oxg_status oxg_shard_create(int device, uint32_t ksize, int rank, int n_ranks, uint64_t capacity_hint,
+                            uint64_t round_windows, oxg_shard **out);
+oxg_status oxg_shard_destroy(oxg_shard *s);
+/* the shard's own table: every oxg_table_* / oxg_histo / oxg_export / ... call
+ * works on it and sees the keys this rank owns */
+oxg_table *oxg_shard_table(oxg_shard *s);
+oxg_status oxg_shard_info(const oxg_shard *s, int *rank, int *n_ranks, uint32_t *n_parts,
+                          uint64_t *round_windows, uint64_t *exchange_bytes);
+/* 64-byte cudaIpcMemHandle_t of this shard's exchange area */
+oxg_status oxg_shard_export(oxg_shard *s, uint8_t handle_out[64]);
+/* handles = n_ranks * 64 bytes, entry r exported by rank r (entry `rank` ignored) */
+oxg_status oxg_shard_connect(oxg_shard *s, const uint8_t *handles);
+/* all shards of the table live in this process: shards[i] is rank i of n */
+oxg_status oxg_shard_connect_local(oxg_shard *const *shards, int n);
+/* KmerCountTable::consume (src/lib.rs:545-607) for this rank's reads, batch form as
+ * oxg_consume_batch.  *counted = valid k-mers of THIS rank's reads (what the
+ * reference's consume calls would have returned, summed); *absorbed = k-mers counted
+ * into this shard (from every rank's reads).  skip_bad == 0: this rank's reads are
+ * counted up to its first bad window, and the call returns OXG_ERR_BAD_KMER with
+ * err_read / err_pos as in oxg_consume_batch; the other ranks are not affected.
+ * The host variant streams the buffer through a ring of staging buffers. */
+oxg_status oxg_shard_consume_batch(oxg_shard *s, const uint8_t *bases, const uint64_t *offsets,
+                                   uint64_t n_reads, int skip_bad, uint64_t *counted,
+                                   uint64_t *absorbed, int64_t *err_read, uint64_t *err_pos);
+/* same, inputs resident in this shard's HBM; d_offsets[0] must be 0 and d_bases
+ * 16-byte aligned */
+oxg_status oxg_shard_consume_batch_device(oxg_shard *s, const uint8_t *d_bases,
+                                          const uint64_t *d_offsets, uint64_t n_reads,
+                                          uint64_t total_bases, int skip_bad, uint64_t *counted,
+                                          uint64_t *absorbed, int64_t *err_read, uint64_t *err_pos);
+/* time of the last consume call on this shard's stream (device variant: CUDA events;
+ * host variant: wall clock of the call) and its number of exchange rounds */
+oxg_status oxg_shard_last_ms(const oxg_shard *s, float *ms, uint64_t *rounds);
+/* reductions over the whole table (collective; every rank receives the result):
+ * len / sum_counts / min / max (src/lib.rs:492-539,665), histo(zero=False)
+ * (464-488), |A & B| and |A | B| of two tables sharded the same way (610-638),
+ * jaccard (708-722, one f64 divide of the two reduced integers) */
+oxg_status oxg_shard_stats(oxg_shard *s, oxg_stats *out);
+oxg_status oxg_shard_histo(oxg_shard *s, uint64_t *freq, uint64_t *n, uint64_t cap, uint64_t *n_out);
+oxg_status oxg_shard_setop_sizes(oxg_shard *a, oxg_shard *b, uint64_t *inter, uint64_t *uni);
+oxg_status oxg_shard_jaccard(oxg_shard *a, oxg_shard *b, double *out);
+/* order-independent digests of the whole table: out = {len, sum c, xor h,
+ * sum h*c mod 2^64, keys found on a rank that does not own them (must be 0)} */
+oxg_status oxg_shard_digest(oxg_shard *s, uint64_t out[5]);
+/* small all-gather through the exchange headers (collective): every rank gives
+ * len <= 1 MiB bytes, out receives n_ranks * len bytes in rank order */
+oxg_status oxg_shard_allgather(oxg_shard *s, const void *mine, uint32_t len, void *out);
 
 /* ---- synthetic reads for benchmarks ----------------
  * Fills d_bases with n_reads reads of read_len bases drawn from a random genome

@@ -39,7 +39,7 @@ def specialised_ks() -> list[int]:
     import re
 
     text = open(os.path.join(CSRC, "klist.h")).read()
-    body = text[text.index("#define OXG_FOR_EACH_K"):text.index("#define OXG_ROUTE_K")]
+    body = text[text.index("#define OXG_FOR_EACH_K"):]
     return [int(m) for m in re.findall(r"X\((\d+)\)", body)]
 
 

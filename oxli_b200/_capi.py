@@ -69,11 +69,23 @@ SIGNATURES = {
     "oxg_jaccard": (C.c_int, [vp, vp, C.POINTER(C.c_double)]),
     "oxg_cosine": (C.c_int, [vp, vp, C.POINTER(C.c_double)]),
     "oxg_merge": (C.c_int, [vp, vp, u64p, u64p]),
-    "oxg_route_batch_device": (C.c_int, [vp, vp, vp, u64, u64, u64, C.c_int, C.c_int, C.POINTER(vp), u64, vp, vp, u64p,
-                                         C.c_int, C.POINTER(vp), vp, u64p]),
-    "oxg_ipc_export": (C.c_int, [C.c_int, vp, vp]),
-    "oxg_ipc_import": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
-    "oxg_ipc_close": (C.c_int, [C.c_int, vp]),
+    "oxg_shard_create": (C.c_int, [C.c_int, C.c_uint32, C.c_int, C.c_int, u64, u64, C.POINTER(vp)]),
+    "oxg_shard_destroy": (C.c_int, [vp]),
+    "oxg_shard_table": (vp, [vp]),
+    "oxg_shard_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint32), u64p, u64p]),
+    "oxg_shard_export": (C.c_int, [vp, vp]),
+    "oxg_shard_connect": (C.c_int, [vp, vp]),
+    "oxg_shard_connect_local": (C.c_int, [C.POINTER(vp), C.c_int]),
+    "oxg_shard_consume_batch": (C.c_int, [vp, vp, vp, u64, C.c_int, u64p, u64p, C.POINTER(C.c_int64), u64p]),
+    "oxg_shard_consume_batch_device": (C.c_int, [vp, vp, vp, u64, u64, C.c_int, u64p, u64p, C.POINTER(C.c_int64), u64p]),
+    "oxg_shard_last_ms": (C.c_int, [vp, C.POINTER(C.c_float), u64p]),
+    "oxg_shard_stats": (C.c_int, [vp, C.POINTER(oxg_stats)]),
+    "oxg_shard_histo": (C.c_int, [vp, vp, vp, u64, u64p]),
+    "oxg_shard_setop_sizes": (C.c_int, [vp, vp, u64p, u64p]),
+    "oxg_shard_jaccard": (C.c_int, [vp, vp, C.POINTER(C.c_double)]),
+    "oxg_shard_digest": (C.c_int, [vp, vp]),
+    "oxg_shard_allgather": (C.c_int, [vp, vp, C.c_uint32, vp]),
+    "oxg_table_digest": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "oxg_synth_reads_device": (C.c_int, [C.c_int, vp, u64, C.c_uint32, u64, u64, u64, C.c_uint32, C.c_uint32]),
     "oxg_pinned_alloc": (C.c_int, [u64, C.POINTER(vp)]),
     "oxg_pinned_free": (C.c_int, [vp]),
@@ -299,6 +311,12 @@ class Table:
         check(lib.oxg_last_consume_pass_ms(self._h, C.byref(a), C.byref(b)))
         return float(a.value), float(b.value)
 
+    def device_digest(self, n_ranks: int = 1, rank: int = 0) -> dict:
+        """The same digests computed by one scan on the device (oxg_table_digest)."""
+        out = (u64 * 5)()
+        check(lib.oxg_table_digest(self._h, n_ranks, rank, out))
+        return {"n": int(out[0]), "sum": int(out[1]), "xor": int(out[2]), "sum_hc": int(out[3]), "foreign": int(out[4])}
+
     def digest(self) -> dict:
         """Order-independent digests of the (hash, count) multiset (test helper)."""
         k, v = self.export(1)
@@ -336,21 +354,111 @@ def d2h(dst: np.ndarray, d_src: int, device: int = 0) -> None:
     check(lib.oxg_memcpy_d2h(device, dst.ctypes.data, d_src, dst.nbytes))
 
 
-def ipc_export(d_ptr: int, device: int = 0) -> bytes:
-    buf = (C.c_uint8 * 64)()
-    check(lib.oxg_ipc_export(device, d_ptr, buf))
-    return bytes(buf)
+class Shard:
+    """One shard of a hash-sharded table (low-level wrapper over oxg_shard_*).  Collective calls
+    must be made by every rank; in one process, drive the ranks from one thread each."""
 
+    def __init__(self, ksize: int, rank: int, n_ranks: int, device: int = 0, capacity_hint: int = 0,
+                 round_windows: int = 0):
+        self._h = vp()
+        check(lib.oxg_shard_create(device, ksize, rank, n_ranks, capacity_hint, round_windows, C.byref(self._h)))
+        self.ksize, self.rank, self.n_ranks, self.device = ksize, rank, n_ranks, device
+        # the shard's own table through the plain table API (not owned: never destroyed from here)
+        self.table = Table.__new__(Table)
+        self.table._h = vp(lib.oxg_shard_table(self._h))
+        self.table.ksize, self.table.device = ksize, device
+        self.table.close = lambda: None
 
-def ipc_import(handle: bytes, device: int = 0) -> int:
-    buf = (C.c_uint8 * 64).from_buffer_copy(handle)
-    p = vp()
-    check(lib.oxg_ipc_import(device, buf, C.byref(p)))
-    return int(p.value)
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.oxg_shard_destroy(self._h)
+            self._h = None
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
-def ipc_close(d_ptr: int, device: int = 0) -> None:
-    check(lib.oxg_ipc_close(device, d_ptr))
+    def info(self) -> dict:
+        r, n, p = C.c_int(), C.c_int(), C.c_uint32()
+        w, e = u64(), u64()
+        check(lib.oxg_shard_info(self._h, C.byref(r), C.byref(n), C.byref(p), C.byref(w), C.byref(e)))
+        return {"rank": r.value, "n_ranks": n.value, "n_parts": p.value, "round_windows": w.value, "exchange_bytes": e.value}
+
+    def export_handle(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        check(lib.oxg_shard_export(self._h, buf))
+        return bytes(buf)
+
+    def connect(self, handles: list[bytes]):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.n_ranks
+        check(lib.oxg_shard_connect(self._h, C.c_char_p(blob)))
+
+    @staticmethod
+    def connect_local(shards: list["Shard"]):
+        arr = (vp * len(shards))(*[s._h for s in shards])
+        check(lib.oxg_shard_connect_local(arr, len(shards)))
+
+    def consume_batch(self, bases: np.ndarray, offsets: np.ndarray, skip_bad: bool = True):
+        """Returns (status, counted, absorbed, err_read, err_pos)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        cn, ab, er, ep = u64(), u64(), C.c_int64(), u64()
+        st = lib.oxg_shard_consume_batch(self._h, _ptr(bases), _ptr(offsets), len(offsets) - 1, 1 if skip_bad else 0,
+                                         C.byref(cn), C.byref(ab), C.byref(er), C.byref(ep))
+        if st not in (OK, ERR_BAD_KMER):
+            check(st)
+        return st, int(cn.value), int(ab.value), int(er.value), int(ep.value)
+
+    def consume_batch_device(self, d_bases: int, d_offsets: int, n_reads: int, total_bases: int, skip_bad: bool = True):
+        cn, ab, er, ep = u64(), u64(), C.c_int64(), u64()
+        st = lib.oxg_shard_consume_batch_device(self._h, d_bases, d_offsets, n_reads, total_bases, 1 if skip_bad else 0,
+                                                C.byref(cn), C.byref(ab), C.byref(er), C.byref(ep))
+        if st not in (OK, ERR_BAD_KMER):
+            check(st)
+        return st, int(cn.value), int(ab.value), int(er.value), int(ep.value)
+
+    def last_ms(self) -> tuple[float, int]:
+        ms, n = C.c_float(), u64()
+        check(lib.oxg_shard_last_ms(self._h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def stats(self) -> dict:
+        st = oxg_stats()
+        check(lib.oxg_shard_stats(self._h, C.byref(st)))
+        return {"len": st.len, "sum": st.sum, "min": st.min, "max": st.max}
+
+    def histo(self) -> list[tuple[int, int]]:
+        n = u64()
+        check(lib.oxg_shard_histo(self._h, None, None, 0, C.byref(n)))
+        f = np.empty(max(n.value, 1), dtype=np.uint64)
+        m = np.empty(max(n.value, 1), dtype=np.uint64)
+        # (collective: the sizing call above was one round, this is the second)
+        check(lib.oxg_shard_histo(self._h, _ptr(f), _ptr(m), len(f), C.byref(n)))
+        return [(int(a), int(b)) for a, b in zip(f[: n.value], m[: n.value])]
+
+    def setop_sizes(self, other: "Shard") -> tuple[int, int]:
+        i, u = u64(), u64()
+        check(lib.oxg_shard_setop_sizes(self._h, other._h, C.byref(i), C.byref(u)))
+        return int(i.value), int(u.value)
+
+    def jaccard(self, other: "Shard") -> float:
+        d = C.c_double()
+        check(lib.oxg_shard_jaccard(self._h, other._h, C.byref(d)))
+        return float(d.value)
+
+    def digest(self) -> dict:
+        out = (u64 * 5)()
+        check(lib.oxg_shard_digest(self._h, out))
+        return {"n": int(out[0]), "sum": int(out[1]), "xor": int(out[2]), "sum_hc": int(out[3]), "foreign": int(out[4])}
+
+    def allgather(self, mine: bytes) -> list[bytes]:
+        out = (C.c_uint8 * (len(mine) * self.n_ranks))()
+        check(lib.oxg_shard_allgather(self._h, C.c_char_p(mine), len(mine), out))
+        raw = bytes(out)
+        return [raw[i * len(mine):(i + 1) * len(mine)] for i in range(self.n_ranks)]
 
 
 def synth_reads_device(d_bases: int, n_reads: int, read_len: int, genome_len: int, seed: int,

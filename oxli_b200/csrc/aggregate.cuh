@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
     const uint64_t n_items = s_spill_first[p.n_src];
 
     uint32_t created = 0;
+    uint64_t n_taken = 0;  // occurrences this thread fed into the table (cache or direct)
     auto flush_created = [&]() {
         const uint32_t tot = __reduce_add_sync(0xffffffffu, created);
         if (lane == 0 && tot) atomicAdd((unsigned long long *)&tv.ctrl->size, (unsigned long long)tot);
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
                 if (filter_owner && p.n_ranks > 1 && ok) ok = (int)(h[u] >> p.owner_shift) == p.self_rank;
                 live |= (ok ? 1u : 0u) << u;
             }
+            n_taken += __popc(live);
             take(h, live, full);
         }
         flush_created();
@@ -210,6 +212,8 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
             flush_created();
         }
     }
+    for (int o = 16; o; o >>= 1) n_taken += __shfl_xor_sync(0xffffffffu, n_taken, o);
+    if (lane == 0 && n_taken) atomicAdd((unsigned long long *)&tv.ctrl->absorbed, (unsigned long long)n_taken);
 }
 
 }  // namespace oxg

@@ -4,6 +4,7 @@
 // count table.  Everything is plain CUDA runtime: no torch, no Thrust/CUB.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstddef>
@@ -24,6 +25,7 @@
 #include "aggregate.cuh"
 #include "consume.cuh"
 #include "klist.h"
+#include "shard.cuh"
 #include "tableops.cuh"
 
 using namespace oxg;
@@ -328,7 +330,6 @@ oxg_status drain_deferred(oxg_table *t, uint64_t ov) {
 #define OXG_DECLARE_ENTRY(KK) extern "C" const void *oxg_consume_entry_##KK(int mode);
 OXG_FOR_EACH_K(OXG_DECLARE_ENTRY)
 #undef OXG_DECLARE_ENTRY
-constexpr bool route_k(int k) { return OXG_ROUTE_K(k); }
 const void *specialised_entry(uint32_t k, int mode) {
     switch (k) {
 #define OXG_K_ENTRY(KK) case KK: return oxg_consume_entry_##KK(mode);
@@ -349,7 +350,7 @@ oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
         int per_sm = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
         const uint64_t tiles_per_cta = specialised_k(t->k) ? kThreads / 32 : 1;
-        const uint64_t work = p.n_tiles + (MODE == kModeRoute ? p.absorb_first[p.n_absorb] : 0);
+        const uint64_t work = p.n_tiles;
         return (int)std::max<uint64_t>(1, std::min<uint64_t>((work + tiles_per_cta - 1) / tiles_per_cta, (uint64_t)c->sms * per_sm));
     };
     if (const void *fn = specialised_entry(t->k, MODE)) {
@@ -367,11 +368,8 @@ oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
         void *args[] = {const_cast<ConsumeParams *>(&p)};
         CU(cudaLaunchKernel(fn, dim3(grid_of(fn, dyn)), dim3(kThreads), args, dyn, c->stream));
     } else {
-        if (MODE == kModeRoute) return fail(OXG_ERR_INVALID, "sharded routing is built for k = 21 and 31 only");
-        if constexpr (MODE != kModeRoute) {
-            const size_t smem = generic_smem_bytes(k);
-            consume_generic_kernel<MODE><<<grid_of((const void *)consume_generic_kernel<MODE>, smem), kThreads, smem, c->stream>>>(p);
-        }
+        const size_t smem = generic_smem_bytes(k);
+        consume_generic_kernel<MODE><<<grid_of((const void *)consume_generic_kernel<MODE>, smem), kThreads, smem, c->stream>>>(p);
     }
     LAUNCHED();
     CU(cudaGetLastError());
@@ -1236,6 +1234,26 @@ oxg_status oxg_histo(oxg_table *t, uint64_t *freq, uint64_t *n, uint64_t cap, ui
     return OXG_OK;
 }
 
+oxg_status oxg_table_digest(oxg_table *t, int n_ranks, int rank, uint64_t out[5]) {
+    ENTER(t);
+    if (!out) return fail(OXG_ERR_INVALID, "null argument");
+    if (n_ranks < 1 || (n_ranks & (n_ranks - 1)) || rank < 0 || rank >= n_ranks) return fail(OXG_ERR_INVALID, "bad rank / n_ranks");
+    int lg = 0;
+    while ((1 << lg) < n_ranks) ++lg;
+    CU(cudaMemsetAsync(t->d_ctrl->scratch, 0, 5 * 8, c->stream));
+    digest_kernel<<<grid_for(c, t->cap, kOpThreads, 8), kOpThreads, 0, c->stream>>>(view_of(t, false), 64 - lg, (uint64_t)rank);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    TRY(pull_ctrl(t));
+    const Ctrl *h = t->h_ctrl;
+    for (int i = 0; i < 5; ++i) out[i] = h->scratch[i];
+    if (h->side_present) {  // the out-of-band key 2^64-1 (owner: the last rank)
+        out[0] += 1; out[1] += h->side_count; out[2] ^= kEmpty; out[3] += kEmpty * h->side_count;
+        if (n_ranks > 1 && rank != n_ranks - 1) out[4] += 1;
+    }
+    return OXG_OK;
+}
+
 // ---- export --------------------------------------------------------------------
 
 static oxg_status export_device(oxg_table *t, uint64_t **d_keys, uint64_t **d_vals, uint64_t *n_live) {
@@ -1441,121 +1459,6 @@ oxg_status oxg_merge(oxg_table *dst, oxg_table *src, uint64_t *counts_added, uin
     return OXG_OK;
 }
 
-// ---- multi-GPU routing ------------------------------------------------------------
-
-oxg_status oxg_route_batch_device(oxg_table *t, const uint8_t *d_bases, const uint64_t *d_offsets,
-                                  uint64_t n_reads, uint64_t base_lo, uint64_t base_hi, int n_ranks,
-                                  int self_rank, uint64_t *const *d_out, uint64_t out_cap,
-                                  uint64_t *d_out_counts, uint64_t *out_counts, uint64_t *local_counted,
-                                  int n_absorb, const uint64_t *const *d_absorb, const uint64_t *absorb_n,
-                                  uint64_t *absorbed) {
-    ENTER(t);
-    if (n_ranks < 2 || n_ranks > kMaxRanks || (n_ranks & (n_ranks - 1)))
-        return fail(OXG_ERR_INVALID, "n_ranks must be a power of two in 2..%d (one rank: oxg_consume_batch_device)", kMaxRanks);
-    if (self_rank < 0 || self_rank >= n_ranks) return fail(OXG_ERR_INVALID, "self_rank out of range");
-    if (n_absorb < 0 || n_absorb > kMaxRanks) return fail(OXG_ERR_INVALID, "at most %d absorb segments", kMaxRanks);
-    if (base_hi < base_lo) return fail(OXG_ERR_INVALID, "base_hi < base_lo");
-    if (!route_k((int)t->k)) return fail(OXG_ERR_INVALID, "sharded routing is built for k = 21 and 31 only");
-    if (local_counted) *local_counted = 0;
-    if (absorbed) *absorbed = 0;
-    const uint64_t k = t->k;
-    CU(cudaMemsetAsync(d_out_counts, 0, (size_t)n_ranks * 8, c->stream));
-    t->last_ms = 0.f; t->last_ms_a = 0.f; t->last_ms_b = 0.f; t->last_launches = 0;
-    uint64_t counted = 0, absorbed_total = 0;
-    const uint64_t w_end = base_hi - base_lo >= k ? base_hi - k + 1 : base_lo;  // one past the last window start
-    int lg = 0;
-    while ((1 << lg) < n_ranks) ++lg;
-    uint64_t absorb_total = 0;
-    for (int i = 0; i < n_absorb; ++i) absorb_total += absorb_n[i];
-    uint64_t lo = base_lo;
-    bool first = true;
-    while (lo < w_end || (first && absorb_total)) {
-        const uint64_t tile_base = lo & ~(uint64_t)15;
-        const uint64_t hi = std::min<uint64_t>(w_end, tile_base + kLaunchWindows);
-        const uint32_t tw = tile_width(t->k);
-        const uint64_t n_tiles = hi > tile_base ? (hi - tile_base + tw - 1) / tw : 0;
-        TRY(ensure_dev(&c->d_tile_first, &c->tile_first_cap, std::max<uint64_t>(n_tiles, 1)));
-        if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
-        TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, (hi > lo ? hi - lo : 0) + (first ? absorb_total : 0) + 1));
-        TRY(zero_ctrl_fields(t, kFieldCounted, kLaunchFields));
-        ConsumeParams p{};
-        p.bases = d_bases; p.g0 = 0; p.w_lo = lo; p.w_hi = hi; p.data_end = base_hi;
-        p.tile_base = tile_base; p.n_tiles = n_tiles; p.offsets = d_offsets; p.n_off = n_reads + 1;
-        p.tile_first = c->d_tile_first; p.table = view_of(t, true); p.ksize = t->k;
-        p.owner_shift = 64 - lg;
-        p.self_rank = self_rank;
-        p.n_ranks = n_ranks;
-        for (int r = 0; r < n_ranks; ++r) p.route_out[r] = d_out ? d_out[r] : nullptr;
-        p.route_counts = d_out_counts; p.route_cap = out_cap;
-        p.n_absorb = 0;
-        p.absorb_first[0] = 0;
-        if (first) {
-            for (int i = 0; i < n_absorb; ++i) {
-                if (!absorb_n[i]) continue;
-                p.absorb_ptr[p.n_absorb] = d_absorb[i];
-                p.absorb_n[p.n_absorb] = absorb_n[i];
-                p.absorb_first[p.n_absorb + 1] = p.absorb_first[p.n_absorb] + (absorb_n[i] + kWarpTile - 1) / kWarpTile;
-                ++p.n_absorb;
-            }
-        }
-        if (n_tiles) {
-            tile_first_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, c->stream>>>(d_offsets, n_reads + 1, tile_base, n_tiles, tw, c->d_tile_first);
-            LAUNCHED();
-        }
-        CU(cudaEventRecord(c->ev_t0, c->stream));
-        TRY(launch_consume<kModeRoute>(t, p));
-        CU(cudaEventRecord(c->ev_t1, c->stream));
-        TRY(pull_ctrl(t));
-        float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
-        t->last_ms += ms; t->last_launches += 1;
-        counted += t->h_ctrl->counted;
-        absorbed_total += t->h_ctrl->absorbed;
-        const uint64_t ov = t->h_ctrl->overflow;
-        if (ov) TRY(drain_deferred(t, ov));
-        lo = std::max(hi, lo);
-        first = false;
-    }
-    if (out_counts) {
-        CU(cudaMemcpyAsync(out_counts, d_out_counts, (size_t)n_ranks * 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        for (int r = 0; r < n_ranks; ++r)
-            if (out_counts[r] > out_cap) return fail(OXG_ERR_TOO_SMALL, "outgoing list for rank %d overran (%llu > %llu)", r, (unsigned long long)out_counts[r], (unsigned long long)out_cap);
-    }
-    if (local_counted) *local_counted = counted;
-    if (absorbed) *absorbed = absorbed_total;
-    return OXG_OK;
-}
-
-oxg_status oxg_ipc_export(int device, void *d_ptr, uint8_t handle_out[64]) {
-    DeviceCtx *c;
-    TRY(get_ctx(device, &c));
-    CU(cudaSetDevice(c->dev));
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
-    cudaIpcMemHandle_t h;
-    CU(cudaIpcGetMemHandle(&h, d_ptr));
-    memcpy(handle_out, &h, 64);
-    return OXG_OK;
-}
-
-oxg_status oxg_ipc_import(int device, const uint8_t handle[64], void **d_ptr_out) {
-    DeviceCtx *c;
-    TRY(get_ctx(device, &c));
-    CU(cudaSetDevice(c->dev));
-    cudaIpcMemHandle_t h;
-    memcpy(&h, handle, 64);
-    CU(cudaIpcOpenMemHandle(d_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
-    return OXG_OK;
-}
-
-oxg_status oxg_ipc_close(int device, void *d_ptr) {
-    DeviceCtx *c;
-    TRY(get_ctx(device, &c));
-    CU(cudaSetDevice(c->dev));
-    CU(cudaIpcCloseMemHandle(d_ptr));
-    return OXG_OK;
-}
-
 // ---- synthetic reads, memory helpers ------------------------------------------------
 
 oxg_status oxg_synth_reads_device(int device, uint8_t *d_bases, uint64_t n_reads, uint32_t read_len,
@@ -1612,3 +1515,5 @@ oxg_status oxg_memcpy_d2h(int device, void *dst, const void *d_src, uint64_t byt
 }
 
 }  // extern "C"
+
+#include "capi_shard.inc"

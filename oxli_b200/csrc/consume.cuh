@@ -50,8 +50,7 @@ enum Mode : int {
     kModeCount = 0,    // hash + count into the table
     kModeHash = 1,     // hash only, write one u64 per window (0 = bad window)
     kModeFirstBad = 2, // error-mode pre-scan: smallest in-read window holding a bad byte
-    kModeRoute = 3,    // multi-GPU: count hashes owned by this rank, append the rest per owner
-    kModePart = 4      // hash + scatter into per-CTA fragments, one per table partition (pass A)
+    kModePart = 3      // hash + scatter into per-CTA fragments, one per table partition (pass A)
 };
 
 struct ConsumeParams {
@@ -67,20 +66,10 @@ struct ConsumeParams {
     TableView table;
     uint64_t *hashes_out;  // kModeHash: hashes_out[w - w_lo]
     uint32_t ksize;        // generic kernel only
-    // kModeRoute
-    int owner_shift;       // owner(h) = h >> owner_shift
+    // sharding (kModePart): owner(h) = h >> owner_shift
+    int owner_shift;
     int self_rank;
     int n_ranks;
-    uint64_t *route_out[kMaxRanks];
-    uint64_t *route_counts;
-    uint64_t route_cap;
-    // hashes received from other ranks (previous chunk), absorbed by the same launch:
-    // segment i holds absorb_n[i] hashes; blocks of kWarpTile hashes are numbered across
-    // segments, segment i starting at block absorb_first[i]
-    const uint64_t *absorb_ptr[kMaxRanks];
-    uint64_t absorb_n[kMaxRanks];
-    uint64_t absorb_first[kMaxRanks + 1];
-    int n_absorb;
     // kModePart (pass A of the partitioned pipeline, see aggregate.cuh).  Destination of hash h:
     //   dest = owner(h) * n_parts + ((h * phi) >> part_shift)      owner(h) = h >> owner_shift, 0 with one rank
     // so a destination is (rank, contiguous segment of that rank's table).  Every CTA owns one
@@ -320,7 +309,7 @@ __device__ __forceinline__ void slow_round(const TableView &tv, SlowQueue &q, bo
 // first version used 2048-window CTA tiles; ncu showed 30 % of all stall samples
 // at the CTA barrier waiting for the one warp stuck in a long probe.)
 template <int K, int MODE>
-__global__ void __launch_bounds__(kThreads, (MODE == kModeRoute || K > 32) ? 2 : OXG_MIN_CTAS) consume_kernel(const ConsumeParams p) {
+__global__ void __launch_bounds__(kThreads, K > 32 ? 2 : OXG_MIN_CTAS) consume_kernel(const ConsumeParams p) {
     static_assert(K >= 1 && K <= 64, "specialised kernel covers k <= 64");
     constexpr int Q = 8 * ((K + 7 + 7) / 8);  // bytes a thread pulls per strand
     constexpr int BL = ((kWarpTile - 8 + Q) + 15) / 16 * 16;
@@ -331,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, (MODE == kModeRoute || K > 32) ? 2 :
     constexpr uint64_t MK = (K == 64) ? ~0ULL : ((1ULL << K) - 1);
     constexpr uint64_t MK1 = (1ULL << (K - 1)) - 1;
     constexpr uint64_t TAILMASK = (K % 8) ? (~0ULL >> (8 * (8 - K % 8))) : ~0ULL;
-    constexpr bool kCounts = MODE == kModeCount || MODE == kModeRoute;
+    constexpr bool kCounts = MODE == kModeCount;
     constexpr int kWarps = kThreads / 32;
     static_assert(NV <= 32 && NE <= 32, "one lane per staged vector / mask word");
 
@@ -344,10 +333,9 @@ __global__ void __launch_bounds__(kThreads, (MODE == kModeRoute || K > 32) ? 2 :
     __shared__ __align__(16) uint8_t s_raw_all[kWarps][2][BL];
     __shared__ __align__(8) uint64_t s_off_all[kWarps][2][32];
     // dynamic shared memory (see consume_dyn_smem): per warp the slow queue (keys + skip
-    // bytes) and, when routing, the gather buffer for outgoing hashes
+    // bytes) when counting; the per-destination fill counters when scattering
     extern __shared__ __align__(16) uint8_t dyn_smem[];
-    constexpr int kDynPerWarp = kQueueCap * 9 + (MODE == kModeRoute ? kWarpTile * 8 : 0);
-    __shared__ __align__(8) uint64_t s_route_all[MODE == kModeRoute ? kWarps : 1][MODE == kModeRoute ? 2 * kMaxRanks + 1 + kWarpTile / 8 : 1];
+    constexpr int kDynPerWarp = kQueueCap * 9;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *s_fw = s_fw_all[warp], *s_rc = s_rc_all[warp];
@@ -356,7 +344,6 @@ __global__ void __launch_bounds__(kThreads, (MODE == kModeRoute || K > 32) ? 2 :
     uint64_t n_counted = 0;
     uint64_t first_bad = ~0ULL;
 
-    uint64_t n_absorbed = 0;
     uint8_t *dyn = dyn_smem + (kCounts ? warp * kDynPerWarp : 0);
     // pass A: one fill counter per destination, shared by the CTA's warps, alive for the whole launch
     uint32_t *s_fill = reinterpret_cast<uint32_t *>(dyn_smem);
@@ -376,7 +363,6 @@ __global__ void __launch_bounds__(kThreads, (MODE == kModeRoute || K > 32) ? 2 :
         created = 0;
     };
     bool tiles_left = true;
-    bool absorb_left = MODE == kModeRoute && p.n_absorb > 0;
 
     const uint64_t stream_policy = l2_evict_first_policy();
 #if OXG_BULK_STAGE
@@ -435,33 +421,7 @@ __global__ void __launch_bounds__(kThreads, (MODE == kModeRoute || K > 32) ? 2 :
     }
     cp_async_commit();
 
-    while (tiles_left || absorb_left) {
-        if (MODE == kModeRoute && absorb_left) {
-            // one block of hashes that other ranks routed here (they were stored into this
-            // GPU's receive regions by the peers' previous launch)
-            uint64_t b = 0;
-            if (lane == 0) b = atomicAdd((unsigned long long *)&p.table.ctrl->absorb_counter, 1ULL);
-            b = __shfl_sync(0xffffffffu, b, 0);
-            if (b >= p.absorb_first[p.n_absorb]) {
-                absorb_left = false;
-            } else {
-                int seg = 0;
-                while (b >= p.absorb_first[seg + 1]) ++seg;
-                const uint64_t off = (b - p.absorb_first[seg]) * kWarpTile;
-                uint64_t h[kWPT];
-#pragma unroll
-                for (int j = 0; j < kWPT; ++j) {
-                    const uint64_t i = off + j * 32 + lane;
-                    h[j] = i < p.absorb_n[seg] ? __ldcs(p.absorb_ptr[seg] + i) : 0;
-                }
-                const bool full = __ldcg(&p.table.ctrl->size) >= p.table.limit;
-                while (queue.n > kQueueCap - kWPT * 32) slow_round(p.table, queue, full, created);
-                count_fast8(p.table, h, queue, n_absorbed);
-                slow_round(p.table, queue, full, created);
-                flush_created();
-            }
-        }
-        if (!tiles_left) continue;
+    while (tiles_left) {
         const uint64_t t = t_cur;
         if (t >= p.n_tiles) { tiles_left = false; cp_async_wait<0>(); continue; }
         const uint64_t w0 = p.tile_base + t * kWarpTile;
@@ -636,55 +596,6 @@ __global__ void __launch_bounds__(kThreads, (MODE == kModeRoute || K > 32) ? 2 :
                 for (int j = 0; j < kWPT; ++j)
                     if (gp0 + j >= p.w_lo && gp0 + j < p.w_hi) p.hashes_out[gp0 + j - p.w_lo] = h[j];
             } else if (kCounts) {
-                if (MODE == kModeRoute) {
-                    // Hashes owned by another rank go to that rank's outgoing list -- which may
-                    // live in the owner's HBM (peer memory): then these stores ARE the exchange.
-                    // Per warp tile: shared-memory counters rank the hashes per owner, one global
-                    // atomic per owner reserves the run, the hashes are gathered per owner in
-                    // shared memory and written out by consecutive lanes, so every store
-                    // instruction covers up to 256 contiguous bytes per owner (full-size NVLink
-                    // packets instead of scattered 8-byte writes).
-                    uint32_t *s_rcnt = reinterpret_cast<uint32_t *>(s_route_all[warp]);        // [kMaxRanks]
-                    uint32_t *s_rpre = s_rcnt + kMaxRanks;                                     // [kMaxRanks + 1]
-                    uint64_t *s_rbase = s_route_all[warp] + kMaxRanks + 1;                     // [kMaxRanks]
-                    uint64_t *s_stage = reinterpret_cast<uint64_t *>(dyn + kQueueCap * 9);
-                    uint8_t *s_owner = reinterpret_cast<uint8_t *>(s_route_all[warp] + 2 * kMaxRanks + 1);  // [kWarpTile]
-                    if (lane < kMaxRanks) s_rcnt[lane] = 0;
-                    __syncwarp();
-                    uint32_t slot_in_run[kWPT];
-#pragma unroll
-                    for (int j = 0; j < kWPT; ++j) {
-                        const int owner = (int)(h[j] >> p.owner_shift);
-                        if (h[j] != 0 && owner != p.self_rank) slot_in_run[j] = atomicAdd(&s_rcnt[owner], 1u);
-                    }
-                    __syncwarp();
-                    if (lane < p.n_ranks && s_rcnt[lane])
-                        s_rbase[lane] = atomicAdd((unsigned long long *)&p.route_counts[lane], (unsigned long long)s_rcnt[lane]);
-                    if (lane == 0) {
-                        uint32_t run = 0;
-                        for (int o = 0; o < p.n_ranks; ++o) { s_rpre[o] = run; run += s_rcnt[o]; }
-                        s_rpre[p.n_ranks] = run;
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int j = 0; j < kWPT; ++j) {
-                        const int owner = (int)(h[j] >> p.owner_shift);
-                        if (h[j] != 0 && owner != p.self_rank) {
-                            const uint32_t at = s_rpre[owner] + slot_in_run[j];
-                            s_stage[at] = h[j];
-                            s_owner[at] = (uint8_t)owner;
-                            h[j] = 0;
-                        }
-                    }
-                    __syncwarp();
-                    const uint32_t n_out = s_rpre[p.n_ranks];
-                    for (uint32_t i = lane; i < n_out; i += 32) {
-                        const int owner = s_owner[i];
-                        const uint64_t at = s_rbase[owner] + (i - s_rpre[owner]);
-                        if (at < p.route_cap) p.route_out[owner][at] = s_stage[i];
-                    }
-                    __syncwarp();
-                }
                 while (queue.n > kQueueCap - kWPT * 32) slow_round(p.table, queue, full, created);
                 count_fast8(p.table, h, queue, n_counted);
                 slow_round(p.table, queue, full, created);
@@ -718,11 +629,6 @@ __global__ void __launch_bounds__(kThreads, (MODE == kModeRoute || K > 32) ? 2 :
         for (int o = 16; o; o >>= 1) n_counted += __shfl_xor_sync(0xffffffffu, n_counted, o);
         if (lane == 0 && n_counted)
             atomicAdd((unsigned long long *)&p.table.ctrl->counted, (unsigned long long)n_counted);
-        if (MODE == kModeRoute) {
-            for (int o = 16; o; o >>= 1) n_absorbed += __shfl_xor_sync(0xffffffffu, n_absorbed, o);
-            if (lane == 0 && n_absorbed)
-                atomicAdd((unsigned long long *)&p.table.ctrl->absorbed, (unsigned long long)n_absorbed);
-        }
     }
 }
 
@@ -847,7 +753,7 @@ namespace oxg {
 // dynamic shared memory a specialised consume launch needs
 inline size_t consume_dyn_smem(int mode, uint32_t n_dest = 0) {
     if (mode == kModePart) return (size_t)n_dest * 4;
-    if (mode != kModeCount && mode != kModeRoute) return 0;
-    return (size_t)(kThreads / 32) * (kQueueCap * 9 + (mode == kModeRoute ? kWarpTile * 8 : 0));
+    if (mode != kModeCount) return 0;
+    return (size_t)(kThreads / 32) * (kQueueCap * 9);
 }
 }  // namespace oxg

@@ -18,9 +18,6 @@ extern "C" __attribute__((visibility("hidden"))) const void *OXG_CAT(oxg_consume
     case kModeHash: return reinterpret_cast<const void *>(&consume_kernel<OXG_INST_K, kModeHash>);
     case kModeFirstBad: return reinterpret_cast<const void *>(&consume_kernel<OXG_INST_K, kModeFirstBad>);
     case kModePart: return reinterpret_cast<const void *>(&consume_kernel<OXG_INST_K, kModePart>);
-#if OXG_ROUTE_K(OXG_INST_K)
-    case kModeRoute: return reinterpret_cast<const void *>(&consume_kernel<OXG_INST_K, kModeRoute>);
-#endif
     default: return nullptr;
     }
 }

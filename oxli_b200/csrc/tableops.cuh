@@ -238,6 +238,28 @@ __global__ void stats_kernel(TableView t, uint64_t *__restrict__ dense, uint64_t
             if (bins[i]) atomicAdd((unsigned long long *)&dense[i], (unsigned long long)bins[i]);
 }
 
+// Order-independent digests of the (key, count) multiset, for parity checks at sizes where
+// nothing can be exported: scratch [0]=len [1]=sum c [2]=xor h [3]=sum h*c (wrapping)
+// [4]=keys whose owner (h >> owner_shift) differs from `rank` (owner_shift 64: not sharded).
+__global__ void digest_kernel(TableView t, int owner_shift, uint64_t rank) {
+    uint64_t len = 0, sum = 0, x = 0, hc = 0, foreign = 0;
+    for (uint64_t i = gtid(); i < t.cap; i += gstride()) {
+        const ulonglong2 s = t.slots[i];
+        if (s.x == kEmpty) continue;
+        ++len; sum += s.y; x ^= s.x; hc += s.x * s.y;
+        if (owner_shift < 64 && (s.x >> owner_shift) != rank) ++foreign;
+    }
+    len = warp_sum(len); sum = warp_sum(sum); hc = warp_sum(hc); foreign = warp_sum(foreign);
+    for (int o = 16; o; o >>= 1) x ^= __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0 && len) {
+        atomicAdd((unsigned long long *)&t.ctrl->scratch[0], (unsigned long long)len);
+        atomicAdd((unsigned long long *)&t.ctrl->scratch[1], (unsigned long long)sum);
+        atomicXor((unsigned long long *)&t.ctrl->scratch[2], (unsigned long long)x);
+        atomicAdd((unsigned long long *)&t.ctrl->scratch[3], (unsigned long long)hc);
+        if (foreign) atomicAdd((unsigned long long *)&t.ctrl->scratch[4], (unsigned long long)foreign);
+    }
+}
+
 // ---- ordered export: hashes / dump / __iter__ (src/lib.rs:330-381, 517-521, 658-662)
 // pass 1: live slots per chunk of kExportChunk slots
 __global__ void export_count_kernel(const ulonglong2 *__restrict__ slots, uint64_t cap,

@@ -1,33 +1,23 @@
-"""Hash-sharded k-mer counting across the GPUs of one node.
+"""Hash-sharded k-mer count table across the GPUs of one node: the Python face of the
+`oxg_shard_*` entry points (include/oxli_b200.h).
 
-One process per GPU (torch.distributed; NCCL over NVLink on GPUs, gloo in the
-CPU tests of the host logic).  The table is sharded by the high bits of the
-hash -- owner(h) = h >> (64 - log2 N) -- exactly as BASELINE.json's north_star
-prescribes.  Per batch every rank
+The table is sharded by the high bits of the hash -- owner(h) = h >> (64 - log2 N) -- as
+BASELINE.json's north_star prescribes; every rank hashes its own reads, leaves the hashes in
+fragments per (owner, table partition) in its own HBM, and each owner's aggregation kernel
+pulls its fragments from all ranks over NVLink (peer-mapped memory) and counts them.  All of
+that, including the rank-to-rank flags and the reductions (len / sum / min / max, histo,
+|A & B|, jaccard: reference src/lib.rs:464-539, 610-638, 708-722), lives in the C library.
 
-  1. hashes its own reads; hashes it owns are counted straight into its shard
-     by the same kernel, the others are appended to one outgoing list per owner
-     (oxg_route_batch_device),
-  2. exchanges list lengths, then the lists themselves (all-to-all of u64
-     hashes, issued as one grouped batch of send/recv),
-  3. counts what it received (oxg_count_hashes_device).
+Nothing here imports torch.  A launcher (bench.py, the tests, a user's torchrun script)
+provides ONE thing: `exchange(blob: bytes) -> list[bytes]`, an all-gather of a 64-byte CUDA IPC
+handle among the ranks at construction time -- any transport will do (torch.distributed,
+MPI, a pipe).  Ranks that live in one process use `ShardedTable.local(...)` instead.
 
-Reductions over the sharded table need no data exchange beyond scalars or the
-small sparse histogram, because shards hold disjoint key sets:
-len / sum -> SUM, min / max -> MIN / MAX, histo -> per-frequency SUM,
-|A n B| -> SUM of per-shard intersections (both tables use the same owner
-function), jaccard -> one f64 divide of the two reduced integers
-(reference: src/lib.rs:464-539, 610-638, 708-722; merge primitive 778-837).
-
-The compute backend is injected (`engine`), so the exchange / reduction logic is
-testable with world_size 2 on CPU; the product engine is `CudaShardEngine`.
+The per-rank engine is injectable, so the host-side logic in this file (owner function, the
+split of a read set among ranks, zero-filled histograms, error mapping) is testable on CPU
+with world_size 2 over gloo; the product engine is `_capi.Shard`.
 """
 from __future__ import annotations
-
-import json
-import os
-import time
-from dataclasses import dataclass
 
 import numpy as np
 
@@ -37,428 +27,99 @@ def owner_of(h: np.ndarray | int, world: int):
     if world == 1:
         return h * 0 if isinstance(h, np.ndarray) else 0
     shift = 64 - (world.bit_length() - 1)
-    return (np.asarray(h, dtype=np.uint64) >> np.uint64(shift)).astype(np.int64) if isinstance(h, np.ndarray) else int(h) >> shift
+    if isinstance(h, np.ndarray):
+        return (np.asarray(h, dtype=np.uint64) >> np.uint64(shift)).astype(np.int64)
+    return int(h) >> shift
 
 
-@dataclass
-class RouteResult:
-    local_counted: int          # k-mers counted directly into this rank's shard
-    outgoing: list              # per destination rank: 1-D int64 tensor of hashes (empty for self)
+def split_reads(n_reads: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block of a read set that rank `rank` ingests (any split works: counts add)."""
+    return n_reads * rank // world, n_reads * (rank + 1) // world
 
 
-class CudaShardEngine:
-    """Per-rank compute on one GPU through the C ABI (no torch in the library;
-    torch only owns the process group and, in "nccl" mode, the exchange buffers).
+class BadKmerError(ValueError):
+    """consume met a non-ACGT window in error mode (reference: src/lib.rs:593-596)."""
 
-    exchange="p2p" (default): every rank owns a receive buffer with one region per
-    source rank, exported over CUDA IPC; the route kernel of rank s stores the hashes
-    owned by rank d straight into region s of d's buffer over NVLink, so there is no
-    separate bulk exchange -- only the list lengths travel through the process group.
-    exchange="nccl": outgoing lists are staged locally and exchanged with grouped
-    send/recv (the plain-library baseline, also what the CPU tests model)."""
+    def __init__(self, position: int, read: int):
+        super().__init__(f"bad k-mer encountered at position {position}")
+        self.position, self.read = position, read
 
-    def __init__(self, ksize: int, rank: int, world: int, device: int, capacity_hint: int = 0,
-                 out_capacity: int = 0, exchange: str = "p2p"):
-        import torch
 
+class ShardedTable:
+    """Rank-local handle on a hash-sharded count table.  Methods marked (collective) must be
+    called by every rank."""
+
+    def __init__(self, ksize: int, rank: int, world: int, device: int = 0, exchange=None,
+                 capacity_hint: int = 0, round_windows: int = 0, engine=None):
+        assert world >= 1 and world & (world - 1) == 0, "number of shards must be a power of two"
+        self.ksize, self.rank, self.world = ksize, rank, world
+        if engine is None:
+            from . import _capi as capi  # fails loudly without the CUDA library: there is no CPU engine in the product
+
+            engine = capi.Shard(ksize, rank, world, device=device, capacity_hint=capacity_hint, round_windows=round_windows)
+        self.engine = engine
+        if world > 1 and exchange is not None:
+            handles = exchange(engine.export_handle())
+            assert len(handles) == world
+            engine.connect(list(handles))
+
+    @classmethod
+    def local(cls, ksize: int, world: int, devices: list[int], capacity_hint: int = 0, round_windows: int = 0):
+        """All shards in this process (one driver over a node's GPUs, or N > 1 on one GPU in tests).
+        Collective calls must then be issued from one thread per shard."""
         from . import _capi as capi
 
-        self.capi, self.torch = capi, torch
-        self.rank, self.world, self.device = rank, world, device
-        self.table = capi.Table(ksize, device=device, capacity_hint=capacity_hint)
-        self.ksize = ksize
-        self.out_capacity = out_capacity
-        self.exchange = exchange
-        self._out = None
-        self._cap = 0
-        self._recv_base = 0          # p2p: this rank's receive buffer (world regions of _cap entries)
-        self._peer_bases = None      # p2p: imported receive buffers of the peers
-        self._counts = torch.zeros(world, dtype=torch.int64, device=f"cuda:{device}")
+        shards = [cls(ksize, r, world, device=devices[r % len(devices)], capacity_hint=capacity_hint,
+                      round_windows=round_windows) for r in range(world)]
+        capi.Shard.connect_local([s.engine for s in shards])
+        return shards
 
-    # -- nccl mode ------------------------------------------------------------------
-    def _ensure_out(self, cap: int):
-        torch = self.torch
-        if self._out is None or self._out[0].numel() < cap:
-            self._out = [torch.empty(cap if r != self.rank else 1, dtype=torch.int64, device=f"cuda:{self.device}")
-                         for r in range(self.world)]
-        return self._out
+    def close(self):
+        self.engine.close()
 
-    # -- p2p mode -------------------------------------------------------------------
-    def setup_p2p(self, dist, group, cap: int):
-        """(Re)allocate the receive buffer for `cap` hashes per source and swap IPC handles."""
-        capi = self.capi
-        if self._peer_bases is not None and cap <= self._cap:
-            return
-        self.close_p2p()
-        self._cap = cap
-        self._recv_base = capi.device_alloc(2 * self.world * cap * 8, self.device)  # two parities x world regions
-        handles = [None] * self.world
-        dist.all_gather_object(handles, capi.ipc_export(self._recv_base, self.device), group=group)
-        self._peer_bases = [capi.ipc_import(h, self.device) if r != self.rank else self._recv_base
-                            for r, h in enumerate(handles)]
-        dist.barrier(group=group)
+    # -- ingest (collective) ----------------------------------------------------------
+    def consume_batch(self, bases: np.ndarray, offsets: np.ndarray, skip_bad_kmers: bool = True) -> int:
+        """This rank's reads (CSR batch in host memory).  Returns the number of k-mers counted
+        from them, i.e. the sum of what the reference's consume would return per read."""
+        st, counted, absorbed, er, ep = self.engine.consume_batch(bases, offsets, skip_bad_kmers)
+        self.last_absorbed = absorbed
+        if st != 0:
+            raise BadKmerError(ep, er)
+        return counted
 
-    def close_p2p(self):
-        if self._peer_bases is not None:
-            for r, p in enumerate(self._peer_bases):
-                if r != self.rank:
-                    self.capi.ipc_close(p, self.device)
-            self.capi.device_free(self._recv_base, self.device)
-            self._peer_bases, self._recv_base, self._cap = None, 0, 0
+    def consume_batch_device(self, d_bases: int, d_offsets: int, n_reads: int, total_bases: int,
+                             skip_bad_kmers: bool = True) -> int:
+        st, counted, absorbed, er, ep = self.engine.consume_batch_device(d_bases, d_offsets, n_reads, total_bases, skip_bad_kmers)
+        self.last_absorbed = absorbed
+        if st != 0:
+            raise BadKmerError(ep, er)
+        return counted
 
-    def capacity_for(self, total_bases: int) -> int:
-        n_win = max(total_bases - self.ksize + 1, 0)
-        return self.out_capacity or int(n_win / self.world * 1.25) + (1 << 16)
-
-    def route(self, d_bases: int, d_offsets: int, n_reads: int, total_bases: int, base_lo: int = 0,
-              base_hi: int | None = None, parity: int = 0, absorb: list[tuple[int, int]] | None = None) -> RouteResult:
-        """Hash the reads in bytes [base_lo, base_hi) of the batch.  p2p mode: remote hashes
-        land in region (parity, self.rank) of each owner's receive buffer.  `absorb` =
-        [(device pointer, n)] received hash lists the same launch counts as well."""
-        import ctypes as C
-
-        capi = self.capi
-        base_hi = total_bases if base_hi is None else base_hi
-        if self.exchange == "p2p":
-            cap = self._cap
-            ptrs = (C.c_void_p * self.world)(*[self._peer_bases[d] + self.region_offset(parity, self.rank)
-                                               for d in range(self.world)])
-            out = None
-        else:
-            cap = self.capacity_for(base_hi - base_lo)
-            out = self._ensure_out(cap)
-            ptrs = (C.c_void_p * self.world)(*[t.data_ptr() for t in out])
-        absorb = [(p, n) for p, n in (absorb or []) if n]
-        a_ptrs = (C.c_void_p * max(len(absorb), 1))(*[p for p, _ in absorb])
-        a_n = (C.c_uint64 * max(len(absorb), 1))(*[n for _, n in absorb])
-        host_counts = (C.c_uint64 * self.world)()
-        local, absorbed = C.c_uint64(), C.c_uint64()
-        self.torch.cuda.synchronize(self.device)
-        capi.check(capi.lib.oxg_route_batch_device(self.table.handle, d_bases, d_offsets, n_reads, base_lo, base_hi,
-                                                   self.world, self.rank, ptrs, cap, self._counts.data_ptr(),
-                                                   host_counts, C.byref(local), len(absorb), a_ptrs, a_n,
-                                                   C.byref(absorbed)))
-        self.last_absorbed = int(absorbed.value)
-        if out is None:
-            return RouteResult(int(local.value), [int(host_counts[r]) if r != self.rank else 0 for r in range(self.world)])
-        return RouteResult(int(local.value), [out[r][: int(host_counts[r])] if r != self.rank else out[r][:0]
-                                              for r in range(self.world)])
-
-    def region_offset(self, parity: int, source: int) -> int:
-        """Byte offset of receive region (parity, source) inside a rank's receive buffer."""
-        return (parity * self.world + source) * self._cap * 8
-
-    def new_buffer(self, n: int):
-        return self.torch.empty(n, dtype=self.torch.int64, device=f"cuda:{self.device}")
-
-    def count(self, hashes) -> int:
-        if hashes.numel() == 0:
-            return 0
-        self.torch.cuda.synchronize(self.device)
-        return self.table.count_hashes_device(hashes.data_ptr(), hashes.numel(), skip_zero=False)
-
-    def region_ptr(self, parity: int, source: int) -> int:
-        return self._recv_base + self.region_offset(parity, source)
-
-    def count_region(self, parity: int, source: int, n: int) -> int:
-        """p2p: absorb the first n hashes that rank `source` stored into this rank's buffer."""
-        if n == 0:
-            return 0
-        return self.table.count_hashes_device(self.region_ptr(parity, source), n, skip_zero=False)
-
-    def clear(self):
-        self.table.clear()
-
-    # local reductions
+    # -- reductions (collective) ------------------------------------------------------
     def stats(self) -> dict:
-        return self.table.stats()
-
-    def histo(self) -> list[tuple[int, int]]:
-        return self.table.histo()
-
-    def setop_sizes(self, other: "CudaShardEngine") -> tuple[int, int]:
-        return self.table.setop_sizes(other.table)
-
-    def items_sorted(self):
-        return self.table.export(1)
-
-
-class ShardedCounter:
-    """Rank-local handle on a hash-sharded count table."""
-
-    def __init__(self, engine, group=None):
-        import torch.distributed as dist
-
-        self.dist = dist
-        self.engine = engine
-        self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
-        assert self.world & (self.world - 1) == 0, "number of shards must be a power of two"
-        self.last = {}
-
-    # -- ingest -------------------------------------------------------------------
-    def consume_routed(self, routed: RouteResult) -> int:
-        """Exchange the outgoing lists of `routed` and count what arrives.  Returns the
-        number of k-mers this rank's shard absorbed (local + received)."""
-        import torch
-
-        dist, world, rank = self.dist, self.world, self.rank
-        send_n = torch.tensor([t.numel() for t in routed.outgoing], dtype=torch.int64)
-        dev = routed.outgoing[0].device
-        send_n_dev = send_n.to(dev)
-        recv_n_dev = torch.empty_like(send_n_dev)
-        dist.all_to_all_single(recv_n_dev, send_n_dev, group=self.group) if dev.type == "cuda" else \
-            self._all_to_all_counts_p2p(recv_n_dev, send_n_dev)
-        recv_n = recv_n_dev.cpu().tolist()
-        recv = [self.engine.new_buffer(int(recv_n[r])) if r != rank else None for r in range(world)]
-        ops = []
-        for r in range(world):
-            if r == rank:
-                continue
-            if routed.outgoing[r].numel():
-                ops.append(dist.P2POp(dist.isend, routed.outgoing[r], r, self.group))
-            if recv_n[r]:
-                ops.append(dist.P2POp(dist.irecv, recv[r], r, self.group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        absorbed = routed.local_counted
-        for r in range(world):
-            if r != rank and recv_n[r]:
-                absorbed += self.engine.count(recv[r])
-        self.last = {"sent": int(send_n.sum()), "received": int(sum(recv_n)), "local": routed.local_counted}
-        return absorbed
-
-    def _all_to_all_counts_p2p(self, recv_n, send_n):
-        # gloo (CPU tests): lengths travel as a gathered matrix
-        rows = [recv_n.new_empty(self.world) for _ in range(self.world)]
-        self.dist.all_gather(rows, send_n, group=self.group)
-        for r in range(self.world):
-            recv_n[r] = rows[r][self.rank]
-
-    @staticmethod
-    def plan_chunks(h_offsets: np.ndarray, n_reads: int, chunks: int) -> list[int]:
-        """Read indices at which a batch is cut: byte offsets stay 16-byte aligned."""
-        chunks = max(1, min(chunks, n_reads))
-        cuts = [0]
-        for c in range(1, chunks):
-            r = n_reads * c // chunks
-            while r < n_reads and int(h_offsets[r]) % 16:
-                r += 1
-            if r > cuts[-1] and r < n_reads:
-                cuts.append(r)
-        cuts.append(n_reads)
-        return cuts
-
-    def consume_device(self, d_bases: int, d_offsets: int, n_reads: int, total_bases: int,
-                       h_offsets: np.ndarray | None = None, chunks: int = 8, chunk_ready=None) -> int:
-        """Count a device-resident batch of this rank's reads into the sharded table.
-        Returns the number of k-mers this rank's shard absorbed (own + received).
-        chunk_ready(c), if given, is called before chunk c is touched (lets a caller
-        stream the bases in behind the pipeline)."""
-        eng = self.engine
-        if getattr(eng, "exchange", "nccl") != "p2p":
-            return self.consume_routed(eng.route(d_bases, d_offsets, n_reads, total_bases))
-        # Fused exchange, pipelined over chunks of reads.  The route launch of chunk c
-        #   - stores the hashes owned elsewhere straight into the owners' receive regions
-        #     (parity c&1) over NVLink,
-        #   - counts the hashes it owns, and
-        #   - absorbs what the peers delivered during chunk c-1 (parity (c-1)&1),
-        # so hashing, remote stores and the counting of received hashes overlap inside one
-        # kernel.  Only the list lengths go through the process group; that all-to-all is
-        # also the "everyone finished writing chunk c" barrier, and because a rank enters
-        # it only after its own route(c) -- which absorbed chunk c-1 -- returned, parity
-        # c&1 is free again when any rank starts chunk c+2.
-        import torch
-
-        dist = self.dist
-        if h_offsets is None:
-            h_offsets = np.empty(n_reads + 1, dtype=np.uint64)
-            eng.capi.d2h(h_offsets, d_offsets, eng.device)
-        cuts = self.plan_chunks(h_offsets, n_reads, chunks)
-        biggest = max(int(h_offsets[cuts[i + 1]] - h_offsets[cuts[i]]) for i in range(len(cuts) - 1))
-        cap = torch.tensor([eng.capacity_for(biggest), len(cuts) - 1], dtype=torch.int64, device=f"cuda:{eng.device}")
-        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
-        eng.setup_p2p(dist, self.group, int(cap[0].item()))
-        n_rounds = int(cap[1].item())  # ranks may cut differently; everyone runs the same number of rounds
-
-        absorbed, pending, sent, received = 0, [], 0, 0
-        for c in range(n_rounds):
-            if c < len(cuts) - 1:
-                lo, hi = int(h_offsets[cuts[c]]), int(h_offsets[cuts[c + 1]])
-                if chunk_ready is not None:
-                    chunk_ready(c)
-            else:
-                lo = hi = int(h_offsets[n_reads])
-            routed = eng.route(d_bases, d_offsets, n_reads, total_bases, lo, hi, parity=c & 1, absorb=pending)
-            absorbed += routed.local_counted + eng.last_absorbed
-            send_n = torch.tensor(routed.outgoing, dtype=torch.int64, device=f"cuda:{eng.device}")
-            recv_n = torch.empty_like(send_n)
-            dist.all_to_all_single(recv_n, send_n, group=self.group)
-            recv = recv_n.cpu().tolist()
-            pending = [(eng.region_ptr(c & 1, src), int(recv[src])) for src in range(self.world) if src != self.rank]
-            sent += int(sum(routed.outgoing)); received += int(sum(recv))
-        for ptr, n in pending:  # what arrived during the last round
-            if n:
-                absorbed += eng.table.count_hashes_device(ptr, n, skip_zero=False)
-        dist.barrier(group=self.group)  # nobody re-enters and overwrites regions still being read
-        self.last = {"sent": sent, "received": received, "rounds": n_rounds}
-        return absorbed
-
-    # -- reductions ------------------------------------------------------------------
-    def _reduce(self, values: list[int], op) -> list[int]:
-        import torch
-
-        # int64 transport; u64 sums wrap the same way in two's complement
-        t = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v for v in values], dtype=torch.int64)
-        dev = getattr(self.engine, "device", None)
-        if dev is not None and self.dist.get_backend(self.group) == "nccl":
-            t = t.cuda(dev)
-        self.dist.all_reduce(t, op=op, group=self.group)
-        return [int(v) % (1 << 64) for v in t.cpu().tolist()]
-
-    def stats(self) -> dict:
-        s = self.engine.stats()
-        R = self.dist.ReduceOp
-        n, total = self._reduce([s["len"], s["sum"]], R.SUM)
-        # min of an empty shard must not win: use +inf stand-in
-        mn = self._reduce([s["min"] if s["len"] else (1 << 62)], R.MIN)[0]
-        mx = self._reduce([min(s["max"], (1 << 62))], R.MAX)[0]
-        return {"len": n, "sum": total, "min": 0 if n == 0 else mn, "max": 0 if n == 0 else mx}
+        return self.engine.stats()
 
     def __len__(self) -> int:
         return self.stats()["len"]
 
     def histo(self, zero: bool = True) -> list[tuple[int, int]]:
-        parts = [None] * self.world
-        self.dist.all_gather_object(parts, self.engine.histo(), group=self.group)
-        merged: dict[int, int] = {}
-        for part in parts:
-            for f, c in part:
-                merged[f] = merged.get(f, 0) + c
-        sparse = sorted(merged.items())
+        sparse = self.engine.histo()
         if not zero:
             return sparse
+        merged = dict(sparse)
         top = sparse[-1][0] if sparse else 0
         return [(f, merged.get(f, 0)) for f in range(top + 1)]  # src/lib.rs:475-480
 
-    def setop_sizes(self, other: "ShardedCounter") -> tuple[int, int]:
-        inter, _ = self.engine.setop_sizes(other.engine)
-        R = self.dist.ReduceOp
-        i, na, nb = self._reduce([inter, self.engine.stats()["len"], other.engine.stats()["len"]], R.SUM)
-        return i, na + nb - i
+    def setop_sizes(self, other: "ShardedTable") -> tuple[int, int]:
+        return self.engine.setop_sizes(other.engine)
 
-    def jaccard(self, other: "ShardedCounter") -> float:
-        i, u = self.setop_sizes(other)
-        return 1.0 if u == 0 else float(np.float64(i) / np.float64(u))  # src/lib.rs:716-721
+    def jaccard(self, other: "ShardedTable") -> float:
+        return self.engine.jaccard(other.engine)
 
+    def digest(self) -> dict:
+        """{n, sum, xor, sum_hc, foreign} of the whole table; foreign must be 0."""
+        return self.engine.digest()
 
-# ---------------------------------------------------------------------------------
-# bench.py --gpus N (N > 1): weak scaling, every rank brings its own reads
-# ---------------------------------------------------------------------------------
-
-def run_sharded_bench(a, rank: int, world: int, local: int) -> None:
-    import torch
-    import torch.distributed as dist
-
-    from . import _capi as capi
-    from bench import METRIC, UNIT, SEED, ClockSampler, alg_bytes_per_kmer, measured_peak_gbs, workload_name
-
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    n, L, k = a.reads, a.read_len, a.ksize
-    total_bases = n * L
-    kmers_per_rank = n * (L - k + 1)
-    bases_t = torch.empty(total_bases + 64, dtype=torch.uint8, device=f"cuda:{local}")
-    d_bases = bases_t.data_ptr()
-    d_offs = capi.device_alloc((n + 1) * 8, local)
-    capi.synth_reads_device(d_bases, n, L, a.genome, SEED, first_read=rank * n, device=local)
-    h_offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
-    capi.h2d(d_offs, h_offs, local)
-    engine = CudaShardEngine(k, rank, world, local, capacity_hint=(a.table_hint or a.genome) // world + 1024,
-                             exchange=os.environ.get("OXLI_B200_EXCHANGE", "p2p"))
-    sc = ShardedCounter(engine)
-    n_chunks = int(os.environ.get("OXLI_B200_CHUNKS", "8"))
-
-    def step(chunk_ready=None):
-        engine.clear()
-        return sc.consume_device(d_bases, d_offs, n, total_bases, h_offsets=h_offs, chunks=n_chunks,
-                                 chunk_ready=chunk_ready)
-
-    def timed(fn, steps):
-        torch.cuda.synchronize(); dist.barrier()
-        t0 = time.perf_counter()
-        out = 0
-        for _ in range(steps):
-            out = fn()
-        torch.cuda.synchronize(); dist.barrier()
-        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
-        return float(t.item()), out
-
-    absorbed = 0
-    for _ in range(a.warmup):
-        absorbed = step()
-    torch.cuda.synchronize(); dist.barrier()
-    launches0 = int(capi.lib.oxg_launch_count())
-    with ClockSampler(local) as clocks:
-        dt, absorbed = timed(step, a.steps)
-    launches = int(capi.lib.oxg_launch_count()) - launches0
-
-    # end to end: every rank's reads start in pinned host memory; each step streams them to the
-    # GPU chunk by chunk on a copy stream while the pipeline works on the chunks already there
-    e2e = None
-    if not a.no_e2e:
-        h_bases = torch.empty(total_bases, dtype=torch.uint8).pin_memory()
-        h_bases.copy_(bases_t[:total_bases])
-        copy_stream = torch.cuda.Stream(device=local)
-        cuts = ShardedCounter.plan_chunks(h_offs, n, n_chunks)
-
-        def step_e2e():
-            events = []
-            with torch.cuda.stream(copy_stream):
-                for c in range(len(cuts) - 1):
-                    lo, hi = int(h_offs[cuts[c]]), int(h_offs[cuts[c + 1]])
-                    bases_t[lo:hi].copy_(h_bases[lo:hi], non_blocking=True)
-                    ev = torch.cuda.Event(); ev.record(copy_stream); events.append(ev)
-            got = step(chunk_ready=lambda c: events[c].synchronize())
-            return got + 0 * len(sc)  # device -> host read of the result
-
-        step_e2e()
-        dt2, absorbed2 = timed(step_e2e, a.steps)
-        e2e = {"value": kmers_per_rank * world / (dt2 / a.steps), "unit": UNIT,
-               "h2d_bytes_per_step": int(world * (total_bases + (n + 1) * 0 + 16 * n_chunks * world)),
-               "d2h_bytes_per_step": int(world * (n_chunks * (8 * world + 128) + 64)),
-               "ms_per_step": 1e3 * dt2 / a.steps,
-               "timing": "barrier + cuda sync both sides, max over ranks; pinned host -> chunked async H2D inside the step"}
-        assert absorbed2 == absorbed
-
-    tot = torch.tensor([absorbed, launches], dtype=torch.int64, device=f"cuda:{local}")
-    dist.all_reduce(tot)
-    st = sc.stats()
-    if rank == 0:
-        assert int(tot[0]) == kmers_per_rank * world, (int(tot[0]), kmers_per_rank * world)
-        ms = 1e3 * dt / a.steps
-        value = kmers_per_rank * world / (ms / 1e3)
-        peak, peak_src = measured_peak_gbs()
-        balg = alg_bytes_per_kmer(L, k) + 16.0 * (world - 1) / world  # SURVEY.md 8(d): + remote 8-B write and read
-        achieved = balg * value / 1e9
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic",
-            "config": {"workload": workload_name(a, world), "ksize": k, "read_len": L, "reads_per_gpu": n,
-                       "genome_len": a.genome, "distinct_kmers": st["len"], "sharding": f"hash-high-bits x{world}",
-                       "exchange": ("route kernel stores remote hashes into the owner's HBM over NVLink (CUDA IPC peer memory), "
-                                    f"{n_chunks}-chunk pipeline with fused absorb"
-                                    if engine.exchange == "p2p" else "all-to-all of u64 hashes (grouped NCCL send/recv over NVLink)"),
-                       "l2_policy": "inputs (1.5 GB of reads per GPU per step) far exceed the 126 MB L2; no flush needed"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
-                         "frac": achieved / (peak * world), "traffic": None, "alg_bytes_per_kmer": balg,
-                         "peak_source": peak_src + f" x {world} GPUs", "scope": "whole step, all ranks",
-                         "kernel": f"consume_kernel<{k},route>"},
-            "e2e": e2e, "gpu_launches": int(tot[1]), "timing": "barrier + cuda sync both sides, max over ranks",
-            "exchange_last_step_rank0": sc.last, "clocks": clocks.summary(),
-        }), flush=True)
-    dist.destroy_process_group()
+    # -- this rank's shard only ---------------------------------------------------------
+    def local_items_sorted(self):
+        return self.engine.table.export(1)
