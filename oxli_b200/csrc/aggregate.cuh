@@ -134,8 +134,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
         }
     };
     // a contiguous run of n hashes, consumed by one warp
-    auto take_run = [&](const uint64_t *ptr, uint32_t n, bool filter_owner) {
-        const bool full = tv.overflow != nullptr && __ldcg(&tv.ctrl->size) >= tv.limit;
+    auto take_run = [&](const uint64_t *ptr, uint32_t n, bool filter_owner, bool full) {
         for (uint32_t off = 0; off < n; off += 32 * U) {
             uint64_t h[U];
             uint32_t live = 0;
@@ -150,7 +149,6 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
             n_taken += __popc(live);
             take(h, live, full);
         }
-        flush_created();
     };
 
     for (;;) {
@@ -172,13 +170,27 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
             const uint64_t dest = p.dest0 + item / p.groups;
             const uint32_t g = (uint32_t)(item % p.groups);
             const uint32_t n_frag = p.n_ctas * (uint32_t)p.n_src;
-            for (uint32_t f = g + warp * p.groups; f < n_frag; f += kAggWarps * p.groups) {
-                const int s = (int)(f / p.n_ctas);
-                const uint32_t c = f - (uint32_t)s * p.n_ctas;
-                const uint64_t row = dest * p.n_ctas + c;
-                const uint32_t n = __ldg(p.src[s].frag_cnt + row);
-                if (n) take_run(p.src[s].frag + row * p.frag_cap, n, false);
+            const bool full = tv.overflow != nullptr && __ldcg(&tv.ctrl->size) >= tv.limit;
+            // warp w takes the fragments g + (w + kAggWarps * i) * groups; their fill counts are
+            // fetched 32 at a time, one per lane, so that a fragment costs no latency of its own
+            for (uint32_t f0 = g + warp * p.groups; f0 < n_frag; f0 += 32 * kAggWarps * p.groups) {
+                const uint32_t mine = f0 + lane * kAggWarps * p.groups;
+                uint32_t my_n = 0;
+                const uint64_t *my_ptr = nullptr;
+                if (mine < n_frag) {
+                    const int s = (int)(mine / p.n_ctas);
+                    const uint64_t row = dest * p.n_ctas + (mine - (uint32_t)s * p.n_ctas);
+                    my_n = min(__ldg(p.src[s].frag_cnt + row), p.frag_cap);
+                    my_ptr = p.src[s].frag + row * p.frag_cap;
+                }
+                for (int l = 0; l < 32; ++l) {
+                    const uint32_t n = __shfl_sync(0xffffffffu, my_n, l);
+                    const uint64_t *ptr = reinterpret_cast<const uint64_t *>(__shfl_sync(0xffffffffu, (unsigned long long)my_ptr, l));
+                    if (f0 + (uint32_t)l * kAggWarps * p.groups >= n_frag) break;
+                    if (n) take_run(ptr, n, false, full);
+                }
             }
+            flush_created();
         } else {
             // a slice of some source's spill list (hashes of any partition, any owner)
             int s = 0;
@@ -188,7 +200,9 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
             const uint64_t hi = min(n_sp, lo + kSpillSlice);
             constexpr uint32_t kRun = kSpillSlice / kAggWarps;
             const uint64_t a = lo + (uint64_t)warp * kRun;
-            if (a < hi) take_run(p.src[s].spill + a, (uint32_t)min((uint64_t)kRun, hi - a), true);
+            const bool full = tv.overflow != nullptr && __ldcg(&tv.ctrl->size) >= tv.limit;
+            if (a < hi) take_run(p.src[s].spill + a, (uint32_t)min((uint64_t)kRun, hi - a), true, full);
+            flush_created();
         }
         __syncthreads();  // the cache holds every occurrence that did not bypass it
 

@@ -24,6 +24,7 @@
 #include "../../include/oxli_b200.h"
 #include "aggregate.cuh"
 #include "consume.cuh"
+#include "scatter.cuh"
 #include "klist.h"
 #include "shard.cuh"
 #include "tableops.cuh"
@@ -224,6 +225,8 @@ struct oxg_table {
     uint64_t size = 0;       // host mirror of ctrl->size as of the last sync
     bool hinted = false;     // the caller said how many distinct keys to expect
     uint64_t hint_keys = 0;  // ... and this many
+    bool pooled = false;     // slot arrays come from the stream-ordered allocator (shards: no call of
+                             // theirs may synchronise the device while a peer's flag wait is running)
     float last_ms_a = 0.f, last_ms_b = 0.f;  // partitioned pipeline: pass A / pass B share of last_ms
     uint64_t last_new = 0;   // keys created by the previous consume launch (growth look-ahead)
     float last_ms = 0.f;
@@ -264,8 +267,9 @@ constexpr size_t kFieldTile = offsetof(Ctrl, tile_counter) / 8;
 constexpr size_t kLaunchFields = (offsetof(Ctrl, scratch) - offsetof(Ctrl, counted)) / 8;
 constexpr size_t kFieldScratch = offsetof(Ctrl, scratch) / 8;
 
-oxg_status alloc_slots(DeviceCtx *c, uint64_t cap, ulonglong2 **out) {
-    CU(cudaMalloc(out, cap * sizeof(ulonglong2)));  // (cudaMallocAsync pools were 2x slower for growing multi-GB tables)
+oxg_status alloc_slots(DeviceCtx *c, uint64_t cap, ulonglong2 **out, bool pooled = false) {
+    if (pooled) CU(cudaMallocAsync(out, cap * sizeof(ulonglong2), c->stream));
+    else CU(cudaMalloc(out, cap * sizeof(ulonglong2)));  // (cudaMallocAsync pools were 2x slower for growing multi-GB tables)
     init_slots_kernel<<<grid_for(c, cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(*out, cap);
     LAUNCHED();
     CU(cudaGetLastError());
@@ -278,7 +282,7 @@ oxg_status grow_to_fit(oxg_table *t, uint64_t keys) {
     if (want <= t->cap) return OXG_OK;
     DeviceCtx *c = t->ctx;
     ulonglong2 *fresh = nullptr;
-    TRY(alloc_slots(c, want, &fresh));
+    TRY(alloc_slots(c, want, &fresh, t->pooled));
     ulonglong2 *old = t->slots;
     const uint64_t old_cap = t->cap;
     t->slots = fresh;
@@ -289,7 +293,7 @@ oxg_status grow_to_fit(oxg_table *t, uint64_t keys) {
         CU(cudaGetLastError());
     }
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaFree(old));
+    if (t->pooled) CU(cudaFreeAsync(old, c->stream)); else CU(cudaFree(old));
     return OXG_OK;
 }
 
@@ -299,7 +303,7 @@ oxg_status reserve_keys(oxg_table *t, uint64_t extra) { return grow_to_fit(t, t-
 // high-coverage input every new key is deferred many times).  Grow geometrically -- room for
 // at most as many new keys as the table already holds -- and replay; a replay that runs into
 // the limit again defers into the second list and the loop goes round once more.
-oxg_status drain_deferred(oxg_table *t, uint64_t ov) {
+oxg_status drain_deferred(oxg_table *t, uint64_t ov, bool may_allocate = true) {
     DeviceCtx *c = t->ctx;
     if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
     uint64_t prev = ~0ULL;
@@ -310,7 +314,8 @@ oxg_status drain_deferred(oxg_table *t, uint64_t ov) {
         // deferred for a probe run that would not end rather than for load: double regardless
         if (t->cap == cap_before && ov >= prev) TRY(grow_to_fit(t, t->cap));
         prev = ov;
-        TRY(ensure_dev(&c->d_overflow2, &c->overflow2_cap, ov));
+        if (may_allocate) TRY(ensure_dev(&c->d_overflow2, &c->overflow2_cap, ov));
+        else if (c->overflow2_cap < ov) return fail(OXG_ERR_NOMEM, "deferral list too small for the replay");
         TRY(zero_ctrl_fields(t, offsetof(Ctrl, overflow) / 8, 1));
         TableView v = view_of(t, false);
         v.overflow = c->d_overflow2; v.overflow_cap = c->overflow2_cap;
@@ -383,7 +388,8 @@ struct PartPlan {
     uint32_t n_parts = 0, part_bits = 0;   // partitions of one rank's table
     int n_ranks = 1, self_rank = 0, owner_shift = 64;
     uint32_t grid_a = 0;                   // CTAs of pass A = fragments per destination
-    uint32_t frag_cap = 0;                 // entries per fragment
+    uint32_t frag_cap = 0;                 // entries per fragment (multiple of the line)
+    uint32_t line_shift = 4;               // entries staged per destination before a line is written: 2^line_shift
     uint64_t spill_cap = 0;
     uint32_t groups = 1;
     uint32_t n_dest() const { return n_parts * (uint32_t)n_ranks; }
@@ -398,42 +404,65 @@ bool use_partitioned(const oxg_table *t, uint64_t span) {
     return span >= kPartMinWindows;
 }
 
-// Partition count: about 2048 distinct keys per partition, so that the shared-memory table of
-// pass B (8192 slots) holds a partition's keys at load <= 0.3 and duplicates meet there.
-uint32_t choose_parts(const oxg_table *t) {
+// Partition count: about 4096 distinct keys per partition, so that the shared-memory table of
+// pass B (8192 slots) holds a partition's keys at load <= 0.5 and duplicates meet there; at most
+// max_parts, because pass A stages one line per destination in shared memory.
+uint32_t choose_parts(const oxg_table *t, uint32_t max_parts) {
     const uint32_t forced = g_parts_override.load();
-    if (forced >= 2 && forced <= 8192 && !(forced & (forced - 1))) return forced;
+    if (forced >= 2 && !(forced & (forced - 1))) return std::min(forced, std::max(max_parts * 4, 2u));  // (up to 4096 destinations, with shorter lines)
     const uint64_t est = std::max(t->size + t->last_new, t->hint_keys);
-    if (est == 0) return 1024;
+    if (est == 0) return std::min<uint32_t>(1024, max_parts);
     uint64_t parts = 64;
-    while (parts < 4096 && parts * 2048 < est) parts <<= 1;
-    return (uint32_t)parts;
+    while (parts < max_parts && parts * 4096 < est) parts <<= 1;
+    return (uint32_t)std::min<uint64_t>(parts, max_parts);
+}
+
+// dynamic shared memory of scatter_kernel<k> (mirrors scatter_smem_bytes<K>)
+size_t scatter_smem_rt(uint32_t k, uint32_t n_dest, uint32_t line_shift) {
+    const uint32_t q = 8 * ((k + 7 + 7) / 8);
+    const uint32_t bl = ((kWarpTile - 8 + q) + 15) / 16 * 16;
+    return (size_t)n_dest * ((8u << line_shift) + 16) + 16 + (size_t)kScatWarps * (2 * bl + 128);
 }
 
 oxg_status plan_partitioned(oxg_table *t, uint64_t span, uint64_t n_tiles, int n_ranks, int self_rank, PartPlan *out) {
     DeviceCtx *c = t->ctx;
     PartPlan pl;
-    pl.n_parts = choose_parts(t);
+    // destinations are (rank, partition): 1024 of them keep full 128-byte lines staged in pass A
+    pl.n_parts = choose_parts(t, std::max(2u, 1024u / (uint32_t)n_ranks));
     while ((1u << pl.part_bits) < pl.n_parts) ++pl.part_bits;
     pl.n_ranks = n_ranks; pl.self_rank = self_rank;
     int lg = 0;
     while ((1 << lg) < n_ranks) ++lg;
     pl.owner_shift = 64 - lg;
-    const void *fn = specialised_entry(t->k, kModePart);
-    const size_t dyn = consume_dyn_smem(kModePart, pl.n_dest());
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, dyn) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const uint64_t tiles_per_cta = kThreads / 32;
-    pl.grid_a = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n_tiles + tiles_per_cta - 1) / tiles_per_cta, (uint64_t)c->sms * per_sm));
-    // a fragment holds its fair share of the launch's windows plus half again plus a few sectors;
-    // what does not fit (skew) goes to the spill list, which can take the whole launch
+    pl.line_shift = pl.n_dest() <= 1024 ? 4 : pl.n_dest() <= 2048 ? 3 : 2;
+    if (pl.n_dest() > 4096) return fail(OXG_ERR_INVALID, "internal: too many scatter destinations");
+    // one CTA per SM (its staging fills the SM's shared memory); fewer when the launch is small
+    const uint64_t tiles_per_cta = kScatWarps;
+    pl.grid_a = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n_tiles + tiles_per_cta - 1) / tiles_per_cta, (uint64_t)c->sms));
+    // a fragment holds its fair share of the launch's windows plus half again plus four standard
+    // deviations; what does not fit (skew) goes to the spill list, which can take the whole launch
+    const uint64_t line = 1ull << pl.line_shift;
     const uint64_t fair = span / ((uint64_t)pl.n_dest() * pl.grid_a) + 1;
-    pl.frag_cap = (uint32_t)((fair + fair / 2 + 24 + 3) & ~3ull);
+    uint64_t sq = 1;
+    while (sq * sq < fair) ++sq;
+    pl.frag_cap = (uint32_t)((fair + fair / 2 + 4 * sq + line + line - 1) & ~(line - 1));
     pl.spill_cap = span;
     const uint32_t forced_groups = g_groups_override.load();
     pl.groups = forced_groups ? forced_groups : 1;
     if (pl.frag_entries() >> 32) return fail(OXG_ERR_INVALID, "internal: fragment buffer too large for one launch");
     *out = pl;
+    return OXG_OK;
+}
+
+// scatter_kernel needs more than 48 KB of dynamic shared memory: opt in once per k and device
+oxg_status scatter_attr(DeviceCtx *c, uint32_t k) {
+    static std::mutex mu;
+    static std::vector<std::pair<uint32_t, int>> done;
+    std::lock_guard<std::mutex> lk(mu);
+    const std::pair<uint32_t, int> key{k, c->dev};
+    if (std::find(done.begin(), done.end(), key) != done.end()) return OXG_OK;
+    CU(cudaFuncSetAttribute(specialised_entry(k, kModePart), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    done.push_back(key);
     return OXG_OK;
 }
 
@@ -447,17 +476,18 @@ oxg_status ensure_part_buffers(DeviceCtx *c, const PartPlan &pl) {
 
 // pass A: p is a filled-in ConsumeParams (table.ctrl is where `counted` goes)
 oxg_status launch_part_a(oxg_table *t, ConsumeParams p, const PartPlan &pl, uint64_t *d_frag, uint32_t *d_frag_cnt,
-                         uint64_t *d_spill, unsigned long long *d_spill_n) {
+                         uint64_t *d_spill, unsigned long long *d_spill_n, cudaStream_t stream) {
     DeviceCtx *c = t->ctx;
     const void *fn = specialised_entry(t->k, kModePart);
-    const size_t dyn = consume_dyn_smem(kModePart, pl.n_dest());
+    TRY(scatter_attr(c, t->k));
+    const size_t dyn = scatter_smem_rt(t->k, pl.n_dest(), pl.line_shift);
     p.frag = d_frag; p.frag_cnt = d_frag_cnt; p.frag_cap = pl.frag_cap;
-    p.n_parts = pl.n_parts; p.part_shift = 64 - pl.part_bits; p.n_dest = pl.n_dest();
+    p.n_parts = pl.n_parts; p.part_shift = 64 - pl.part_bits; p.n_dest = pl.n_dest(); p.line_shift = pl.line_shift;
     p.n_ranks = pl.n_ranks; p.self_rank = pl.self_rank; p.owner_shift = pl.owner_shift;
     p.spill = d_spill; p.spill_cap = pl.spill_cap; p.spill_n = d_spill_n;
-    CU(cudaMemsetAsync(d_spill_n, 0, 8, c->stream));
+    CU(cudaMemsetAsync(d_spill_n, 0, 8, stream));
     void *args[] = {&p};
-    CU(cudaLaunchKernel(fn, dim3(pl.grid_a), dim3(kThreads), args, dyn, c->stream));
+    CU(cudaLaunchKernel(fn, dim3(pl.grid_a), dim3(kScatThreads), args, dyn, stream));
     LAUNCHED();
     CU(cudaGetLastError());
     return OXG_OK;
@@ -541,7 +571,7 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
         }
         CU(cudaEventRecord(c->ev_t0, c->stream));
         if (part) {
-            TRY(launch_part_a(t, p, pl, c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n));
+            TRY(launch_part_a(t, p, pl, c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n, c->stream));
             CU(cudaEventRecord(c->ev_mid, c->stream));
             const AggSource own{c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n};
             TRY(launch_part_b(t, pl, &own, 1));
@@ -668,7 +698,7 @@ oxg_status oxg_table_destroy(oxg_table *t) {
     std::lock_guard<std::mutex> lk(t->ctx->mu);
     cudaSetDevice(t->ctx->dev);
     cudaStreamSynchronize(t->ctx->stream);
-    cudaFree(t->slots);
+    if (t->pooled) cudaFreeAsync(t->slots, t->ctx->stream); else cudaFree(t->slots);
     cudaFree(t->d_ctrl);
     cudaFreeHost(t->h_ctrl);
     delete t;
@@ -1133,7 +1163,7 @@ oxg_status oxg_cut(oxg_table *t, int mode, uint64_t thresh, uint64_t *n_removed)
     TRY(pull_ctrl(t));
     uint64_t removed = 0;
     ulonglong2 *fresh = nullptr;
-    TRY(alloc_slots(c, t->cap, &fresh));
+    TRY(alloc_slots(c, t->cap, &fresh, t->pooled));
     ulonglong2 *old = t->slots;
     t->slots = fresh;
     TRY(zero_ctrl_fields(t, kFieldScratch, 1));
@@ -1141,7 +1171,7 @@ oxg_status oxg_cut(oxg_table *t, int mode, uint64_t thresh, uint64_t *n_removed)
     LAUNCHED();
     CU(cudaGetLastError());
     TRY(pull_ctrl(t));
-    CU(cudaFree(old));
+    if (t->pooled) CU(cudaFreeAsync(old, c->stream)); else CU(cudaFree(old));
     removed = t->h_ctrl->scratch[0];
     t->h_ctrl->size -= removed;
     if (t->h_ctrl->side_present) {

@@ -72,16 +72,17 @@ struct ConsumeParams {
     int n_ranks;
     // kModePart (pass A of the partitioned pipeline, see aggregate.cuh).  Destination of hash h:
     //   dest = owner(h) * n_parts + ((h * phi) >> part_shift)      owner(h) = h >> owner_shift, 0 with one rank
-    // so a destination is (rank, contiguous segment of that rank's table).  Every CTA owns one
-    // fragment of frag_cap entries per destination: frag[(dest * gridDim.x + blockIdx.x) * frag_cap ..];
-    // a hash whose fragment is full goes to the spill list.  frag_cnt[dest * gridDim.x + blockIdx.x]
-    // = entries written.
+    // so a destination is (rank, contiguous segment of that rank's table).  Every CTA of
+    // scatter_kernel (scatter.cuh) owns one fragment of frag_cap entries per destination:
+    // frag[(dest * gridDim.x + blockIdx.x) * frag_cap ..]; a hash whose fragment is full goes to
+    // the spill list.  frag_cnt[dest * gridDim.x + blockIdx.x] = entries written.
     uint64_t *frag;
     uint32_t *frag_cnt;
     uint32_t frag_cap;
     uint32_t n_parts;        // partitions per rank (power of two, >= 2)
     uint32_t part_shift;     // 64 - log2(n_parts)
     uint32_t n_dest;         // n_ranks * n_parts
+    uint32_t line_shift;     // log2 of the entries staged per destination before a line is written (scatter.cuh)
     uint64_t *spill;
     uint64_t spill_cap;
     unsigned long long *spill_n;
@@ -303,6 +304,119 @@ __device__ __forceinline__ void slow_round(const TableView &tv, SlowQueue &q, bo
     q.n = out;
 }
 
+// Geometry of a warp tile of kWarpTile window starts for one k.
+template <int K>
+struct TileGeom {
+    static constexpr int Q = 8 * ((K + 7 + 7) / 8);  // bytes a thread pulls per strand
+    static constexpr int BL = ((kWarpTile - 8 + Q) + 15) / 16 * 16;
+    static constexpr int NV = BL / 16;
+    static constexpr int NX = Q / 8;
+    static constexpr int NW = (K + 7) / 8;
+    static constexpr int NE = BL / 32 + 3;
+    static constexpr uint64_t MK = (K == 64) ? ~0ULL : ((1ULL << K) - 1);
+    static constexpr uint64_t MK1 = (1ULL << (K - 1)) - 1;
+    static constexpr uint64_t TAILMASK = (K % 8) ? (~0ULL >> (8 * (8 - K % 8))) : ~0ULL;
+};
+
+// Which of the lane's kWPT consecutive windows (starting at tile-relative position lane * kWPT)
+// are counted: inside [w_lo, w_hi), no bad bit in [p, p+K), no end bit in [p, p+K-1).  In the
+// error-mode pre-scan (MODE == kModeFirstBad) nothing is valid; the smallest in-read window
+// holding a bad byte goes to first_bad instead.
+template <int K, int MODE>
+__device__ __forceinline__ uint32_t lane_valid_mask(const ConsumeParams &p, const uint16_t *s_bad, const uint32_t *s_end,
+                                                    uint64_t w0, int lane, uint64_t &first_bad) {
+    constexpr uint64_t MK = TileGeom<K>::MK, MK1 = TileGeom<K>::MK1;
+    const int p0 = lane * kWPT;
+    const uint32_t *bad32 = reinterpret_cast<const uint32_t *>(s_bad);
+    const int wi = p0 >> 5, sh = p0 & 31;
+    // bits [p0, p0 + 7 + K) of the two masks: two 32-bit words hold them up to K = 33,
+    // three up to K = 64 (sh is 0, 8, 16 or 24)
+    const uint64_t mb = (((uint64_t)bad32[wi + 1] << 32) | bad32[wi]) >> sh;
+    const uint64_t me = (((uint64_t)s_end[wi + 1] << 32) | s_end[wi]) >> sh;
+    uint64_t mb_hi = 0, me_hi = 0;  // bits 64.. of the same, K > 33 only
+    if constexpr (K > 33) {
+        mb_hi = ((uint64_t)bad32[wi + 2] << 32) >> sh;  // its bit i is mask bit 32 + i
+        me_hi = ((uint64_t)s_end[wi + 2] << 32) >> sh;
+    }
+    const uint64_t gp0 = w0 + p0;
+
+    uint32_t valid = 0;
+#pragma unroll
+    for (int j = 0; j < kWPT; ++j) {
+        const bool in_range = gp0 + j >= p.w_lo && gp0 + j < p.w_hi;
+        uint64_t vb = mb >> j, ve = me >> j;
+        if constexpr (K > 33) {
+            // mask bits [j, j + 64): the low 64 - sh come from the first two words, the rest
+            // from the third, whose bit i is mask bit 32 + i
+            vb = (mb | (mb_hi << 32)) >> j | (j ? (mb_hi >> 32) << (64 - j) : 0);
+            ve = (me | (me_hi << 32)) >> j | (j ? (me_hi >> 32) << (64 - j) : 0);
+        }
+        const bool in_read = (ve & MK1) == 0;
+        const bool clean = (vb & MK) == 0;
+        if (MODE == kModeFirstBad) {
+            if (in_range && in_read && !clean && gp0 + j + K <= p.data_end)
+                first_bad = min(first_bad, gp0 + j);
+        } else if (in_range && in_read && clean) {
+            valid |= 1u << j;
+        }
+    }
+    return valid;
+}
+
+// Hashes of the lane's valid windows (h[j] stays 0 for the others): canonical strand, then
+// murmur3 x64_128 seed 42 h1 over its K upper-case ASCII bytes.
+template <int K>
+__device__ __forceinline__ void lane_hashes(const uint8_t *s_fw, const uint8_t *s_rc, int p0, uint32_t valid,
+                                            uint64_t (&h)[kWPT]) {
+    constexpr int Q = TileGeom<K>::Q, BL = TileGeom<K>::BL, NX = TileGeom<K>::NX, NW = TileGeom<K>::NW;
+    constexpr uint64_t TAILMASK = TileGeom<K>::TAILMASK;
+    uint64_t F[NX], R[NX];
+    const uint64_t *f64 = reinterpret_cast<const uint64_t *>(s_fw + p0);
+    const uint64_t *r64 = reinterpret_cast<const uint64_t *>(s_rc + BL - p0 - Q);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { F[i] = f64[i]; R[i] = r64[i]; }
+
+    // Straight-line code for all 8 windows (no branch inside, so the compiler can
+    // interleave the independent murmur chains): the strand is chosen from the
+    // byte-swapped leading word; a tie on those 8 bases (probability 4^-8 on random
+    // sequence) is only recorded here and resolved after the block.
+    uint32_t ties = 0;
+    auto hash_one = [&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        constexpr int FO = j, RO = Q - K - j;
+        uint64_t a[NW], b[NW];
+        static_for<NW>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            a[i] = word_at<FO + 8 * i>(F);
+            b[i] = word_at<RO + 8 * i>(R);
+        });
+        a[NW - 1] &= TAILMASK;
+        b[NW - 1] &= TAILMASK;
+        const bool use_rc = bswap64(b[0]) < bswap64(a[0]);
+        if (NW > 1) ties |= (uint32_t)(a[0] == b[0]) << j;
+        uint64_t w[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) w[i] = use_rc ? b[i] : a[i];
+        h[j] = ((valid >> j) & 1u) ? murmur_words<K>(w) : 0;
+    };
+    static_for<kWPT>(hash_one);
+    ties &= valid;
+    if (NW > 1 && ties) {
+        // rare: compare the full k-mers byte by byte from shared memory and redo the hash
+        for (int j = 0; j < kWPT; ++j) {
+            if (!((ties >> j) & 1u)) continue;
+            const uint8_t *fw = s_fw + p0 + j, *rc = s_rc + BL - K - p0 - j;
+            bool use_rc = false;
+            for (int i = 8; i < K; ++i)
+                if (fw[i] != rc[i]) { use_rc = rc[i] < fw[i]; break; }
+            const uint8_t *src = use_rc ? rc : fw;
+            const uint64_t hv = murmur_bytes([&](int i) -> uint64_t { return src[i]; }, K);
+#pragma unroll
+            for (int q = 0; q < kWPT; ++q) if (q == j) h[q] = hv;
+        }
+    }
+}
+
 // Specialised kernel (k <= 32).  Every warp is an independent worker: it pulls
 // tiles of kWarpTile = 256 window starts from an atomic counter, stages them in
 // its private slice of shared memory and only ever executes __syncwarp().  (A
@@ -311,15 +425,7 @@ __device__ __forceinline__ void slow_round(const TableView &tv, SlowQueue &q, bo
 template <int K, int MODE>
 __global__ void __launch_bounds__(kThreads, K > 32 ? 2 : OXG_MIN_CTAS) consume_kernel(const ConsumeParams p) {
     static_assert(K >= 1 && K <= 64, "specialised kernel covers k <= 64");
-    constexpr int Q = 8 * ((K + 7 + 7) / 8);  // bytes a thread pulls per strand
-    constexpr int BL = ((kWarpTile - 8 + Q) + 15) / 16 * 16;
-    constexpr int NV = BL / 16;
-    constexpr int NX = Q / 8;
-    constexpr int NW = (K + 7) / 8;
-    constexpr int NE = BL / 32 + 3;
-    constexpr uint64_t MK = (K == 64) ? ~0ULL : ((1ULL << K) - 1);
-    constexpr uint64_t MK1 = (1ULL << (K - 1)) - 1;
-    constexpr uint64_t TAILMASK = (K % 8) ? (~0ULL >> (8 * (8 - K % 8))) : ~0ULL;
+    constexpr int BL = TileGeom<K>::BL, NV = TileGeom<K>::NV, NE = TileGeom<K>::NE;
     constexpr bool kCounts = MODE == kModeCount;
     constexpr int kWarps = kThreads / 32;
     static_assert(NV <= 32 && NE <= 32, "one lane per staged vector / mask word");
@@ -333,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, K > 32 ? 2 : OXG_MIN_CTAS) consume_k
     __shared__ __align__(16) uint8_t s_raw_all[kWarps][2][BL];
     __shared__ __align__(8) uint64_t s_off_all[kWarps][2][32];
     // dynamic shared memory (see consume_dyn_smem): per warp the slow queue (keys + skip
-    // bytes) when counting; the per-destination fill counters when scattering
+    // bytes) when counting
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     constexpr int kDynPerWarp = kQueueCap * 9;
 
@@ -345,12 +451,6 @@ __global__ void __launch_bounds__(kThreads, K > 32 ? 2 : OXG_MIN_CTAS) consume_k
     uint64_t first_bad = ~0ULL;
 
     uint8_t *dyn = dyn_smem + (kCounts ? warp * kDynPerWarp : 0);
-    // pass A: one fill counter per destination, shared by the CTA's warps, alive for the whole launch
-    uint32_t *s_fill = reinterpret_cast<uint32_t *>(dyn_smem);
-    if (MODE == kModePart) {
-        for (uint32_t i = threadIdx.x; i < p.n_dest; i += kThreads) s_fill[i] = 0;
-        __syncthreads();
-    }
     SlowQueue queue{reinterpret_cast<uint64_t *>(dyn), dyn + kQueueCap * 8, 0};
     uint32_t created = 0;
     bool late = false;  // working on the last quarter of the launch's tiles
@@ -470,128 +570,18 @@ __global__ void __launch_bounds__(kThreads, K > 32 ? 2 : OXG_MIN_CTAS) consume_k
         __syncwarp();
 
         const int p0 = lane * kWPT;
-        const uint32_t *bad32 = reinterpret_cast<const uint32_t *>(s_bad);
-        const int wi = p0 >> 5, sh = p0 & 31;
-        // bits [p0, p0 + 7 + K) of the two masks: two 32-bit words hold them up to K = 33,
-        // three up to K = 64 (sh is 0, 8, 16 or 24)
-        const uint64_t mb = (((uint64_t)bad32[wi + 1] << 32) | bad32[wi]) >> sh;
-        const uint64_t me = (((uint64_t)s_end[wi + 1] << 32) | s_end[wi]) >> sh;
-        uint64_t mb_hi = 0, me_hi = 0;  // bits 64.. of the same, K > 33 only
-        if constexpr (K > 33) {
-            mb_hi = ((uint64_t)bad32[wi + 2] << 32) >> sh;  // its bit i is mask bit 32 + i
-            me_hi = ((uint64_t)s_end[wi + 2] << 32) >> sh;
-        }
         const uint64_t gp0 = w0 + p0;
-
-        uint32_t valid = 0;
-#pragma unroll
-        for (int j = 0; j < kWPT; ++j) {
-            const bool in_range = gp0 + j >= p.w_lo && gp0 + j < p.w_hi;
-            uint64_t vb = mb >> j, ve = me >> j;
-            if constexpr (K > 33) {
-                // mask bits [j, j + 64): the low 64 - sh come from the first two words, the rest
-                // from the third, whose bit i is mask bit 32 + i
-                vb = (mb | (mb_hi << 32)) >> j | (j ? (mb_hi >> 32) << (64 - j) : 0);
-                ve = (me | (me_hi << 32)) >> j | (j ? (me_hi >> 32) << (64 - j) : 0);
-            }
-            const bool in_read = (ve & MK1) == 0;
-            const bool clean = (vb & MK) == 0;
-            if (MODE == kModeFirstBad) {
-                if (in_range && in_read && !clean && gp0 + j + K <= p.data_end)
-                    first_bad = min(first_bad, gp0 + j);
-            } else if (in_range && in_read && clean) {
-                valid |= 1u << j;
-            }
-        }
+        const uint32_t valid = lane_valid_mask<K, MODE>(p, s_bad, s_end, w0, lane, first_bad);
 
         if (MODE != kModeFirstBad) {
             uint64_t h[kWPT] = {};
-            if (valid) {
-                uint64_t F[NX], R[NX];
-                const uint64_t *f64 = reinterpret_cast<const uint64_t *>(s_fw + p0);
-                const uint64_t *r64 = reinterpret_cast<const uint64_t *>(s_rc + BL - p0 - Q);
-#pragma unroll
-                for (int i = 0; i < NX; ++i) { F[i] = f64[i]; R[i] = r64[i]; }
-
-                // Straight-line code for all 8 windows (no branch inside, so the compiler can
-                // interleave the independent murmur chains): the strand is chosen from the
-                // byte-swapped leading word; a tie on those 8 bases (probability 4^-8 on random
-                // sequence) is only recorded here and resolved after the block.
-                uint32_t ties = 0;
-                auto hash_one = [&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    constexpr int FO = j, RO = Q - K - j;
-                    uint64_t a[NW], b[NW];
-                    static_for<NW>([&](auto ic) {
-                        constexpr int i = decltype(ic)::value;
-                        a[i] = word_at<FO + 8 * i>(F);
-                        b[i] = word_at<RO + 8 * i>(R);
-                    });
-                    a[NW - 1] &= TAILMASK;
-                    b[NW - 1] &= TAILMASK;
-                    const bool use_rc = bswap64(b[0]) < bswap64(a[0]);
-                    if (NW > 1) ties |= (uint32_t)(a[0] == b[0]) << j;
-                    uint64_t w[NW];
-#pragma unroll
-                    for (int i = 0; i < NW; ++i) w[i] = use_rc ? b[i] : a[i];
-                    h[j] = ((valid >> j) & 1u) ? murmur_words<K>(w) : 0;
-                };
-                static_for<kWPT>(hash_one);
-                ties &= valid;
-                if (NW > 1 && ties) {
-                    // rare: compare the full k-mers byte by byte from shared memory and redo the hash
-                    for (int j = 0; j < kWPT; ++j) {
-                        if (!((ties >> j) & 1u)) continue;
-                        const uint8_t *fw = s_fw + p0 + j, *rc = s_rc + BL - K - p0 - j;
-                        bool use_rc = false;
-                        for (int i = 8; i < K; ++i)
-                            if (fw[i] != rc[i]) { use_rc = rc[i] < fw[i]; break; }
-                        const uint8_t *src = use_rc ? rc : fw;
-                        const uint64_t hv = murmur_bytes([&](int i) -> uint64_t { return src[i]; }, K);
-#pragma unroll
-                        for (int q = 0; q < kWPT; ++q) if (q == j) h[q] = hv;
-                    }
-                }
-            }
+            if (valid) lane_hashes<K>(s_fw, s_rc, p0, valid, h);
 
             // the next tile's read boundaries (its tile_first entry has arrived by now)
             if (t_nxt < p.n_tiles) prefetch_offsets(tf_next, s_off_all[warp][buf ^ 1]);
             cp_async_commit();
 
-            if (MODE == kModePart) {
-                // One shared-memory atomic hands out the position inside this CTA's fragment of the
-                // destination; the store goes straight to it.  No global atomics, no barrier: the
-                // 8-byte stores of a fragment's sector meet in L2 before they reach DRAM.
-                uint32_t spilled = 0;
-                const uint64_t frag_row = (uint64_t)gridDim.x * p.frag_cap;
-                uint64_t *const my_frag = p.frag + (uint64_t)blockIdx.x * p.frag_cap;
-#pragma unroll
-                for (int j = 0; j < kWPT; ++j) {
-                    if (h[j] == 0) continue;
-                    ++n_counted;
-                    uint32_t dest = (uint32_t)((h[j] * kPhi) >> p.part_shift);
-                    if (p.n_ranks > 1) dest += (uint32_t)(h[j] >> p.owner_shift) * p.n_parts;
-                    const uint32_t pos = atomicAdd(&s_fill[dest], 1u);
-                    if (pos < p.frag_cap) my_frag[dest * frag_row + pos] = h[j];
-                    else spilled |= 1u << j;
-                }
-                if (__any_sync(0xffffffffu, spilled != 0)) {
-                    // skewed input (one k-mer flooding its partition): one reservation per warp tile
-                    const uint32_t mine = __popc(spilled);
-                    uint32_t incl = mine;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += v;
-                    }
-                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(p.spill_n, (unsigned long long)total);
-                    base = __shfl_sync(0xffffffffu, base, 0) + (incl - mine);
-#pragma unroll
-                    for (int j = 0; j < kWPT; ++j)
-                        if ((spilled >> j) & 1u) { if (base < p.spill_cap) p.spill[base] = h[j]; ++base; }
-                }
-            } else if (MODE == kModeHash) {
+            if (MODE == kModeHash) {
 #pragma unroll
                 for (int j = 0; j < kWPT; ++j)
                     if (gp0 + j >= p.w_lo && gp0 + j < p.w_hi) p.hashes_out[gp0 + j - p.w_lo] = h[j];
@@ -616,16 +606,11 @@ __global__ void __launch_bounds__(kThreads, K > 32 ? 2 : OXG_MIN_CTAS) consume_k
         while (queue.n) slow_round(p.table, queue, __ldcg(&p.table.ctrl->size) >= p.table.limit, created);
         flush_created();
     }
-    if (MODE == kModePart) {
-        __syncthreads();  // every warp of the CTA is done scattering
-        for (uint32_t i = threadIdx.x; i < p.n_dest; i += kThreads)
-            p.frag_cnt[(uint64_t)i * gridDim.x + blockIdx.x] = min(s_fill[i], p.frag_cap);
-    }
     if (MODE == kModeFirstBad) {
         for (int o = 16; o; o >>= 1) first_bad = min(first_bad, __shfl_xor_sync(0xffffffffu, first_bad, o));
         if (lane == 0 && first_bad != ~0ULL)
             atomicMin((unsigned long long *)&p.table.ctrl->first_bad, (unsigned long long)first_bad);
-    } else if (kCounts || MODE == kModePart) {
+    } else if (kCounts) {
         for (int o = 16; o; o >>= 1) n_counted += __shfl_xor_sync(0xffffffffu, n_counted, o);
         if (lane == 0 && n_counted)
             atomicAdd((unsigned long long *)&p.table.ctrl->counted, (unsigned long long)n_counted);
@@ -751,8 +736,7 @@ inline size_t generic_smem_bytes(int k) {
 
 namespace oxg {
 // dynamic shared memory a specialised consume launch needs
-inline size_t consume_dyn_smem(int mode, uint32_t n_dest = 0) {
-    if (mode == kModePart) return (size_t)n_dest * 4;
+inline size_t consume_dyn_smem(int mode) {
     if (mode != kModeCount) return 0;
     return (size_t)(kThreads / 32) * (kQueueCap * 9);
 }

@@ -2,6 +2,7 @@
 // Built once per listed k with -DOXG_INST_K=k; exports a single entry point that hands the
 // kernels' addresses to capi.cu, which launches them with cudaLaunchKernel.
 #include "consume.cuh"
+#include "scatter.cuh"
 #include "klist.h"
 
 #ifndef OXG_INST_K
@@ -17,7 +18,7 @@ extern "C" __attribute__((visibility("hidden"))) const void *OXG_CAT(oxg_consume
     case kModeCount: return reinterpret_cast<const void *>(&consume_kernel<OXG_INST_K, kModeCount>);
     case kModeHash: return reinterpret_cast<const void *>(&consume_kernel<OXG_INST_K, kModeHash>);
     case kModeFirstBad: return reinterpret_cast<const void *>(&consume_kernel<OXG_INST_K, kModeFirstBad>);
-    case kModePart: return reinterpret_cast<const void *>(&consume_kernel<OXG_INST_K, kModePart>);
+    case kModePart: return reinterpret_cast<const void *>(&scatter_kernel<OXG_INST_K>);  // pass A of the partitioned pipeline
     default: return nullptr;
     }
 }

@@ -1,0 +1,200 @@
+// scatter.cuh -- pass A of the partitioned pipeline: hash the reads, scatter every hash into
+// the fragment of its destination (see aggregate.cuh for pass B and for why).
+//
+// Replaces the first half of the hot loop of KmerCountTable::consume
+// (/root/reference/src/lib.rs:576-600: the SeqToHashes step); the `count_hash` half happens in
+// pass B.  Validity, canonical strand and hashing are the device functions of consume.cuh.
+//
+// What shapes this kernel is the store side.  A scattered store -- one lane, one sector --
+// costs a B200 SM about seven cycles whatever its width (8, 16 or 32 bytes: 40 G stores/s
+// chip-wide, profiles/r2_microbench_smem_scatter.txt), so "one 8-byte store per hash straight
+// into the destination's fragment" runs at a third of the hashing rate.  Shared-memory atomics
+// and stores, in contrast, cost 0.13-0.45 cycles.  So every destination has a line of
+// 2^line_shift entries (128 bytes at 16) staged in shared memory; hashes are ranked into it
+// with one shared-memory atomic each and a line leaves the SM as ONE full-width coalesced
+// store when it is complete.
+//
+// One CTA of 24 warps per SM works in rounds: every warp hashes one tile of 256 window starts
+// (8 per lane), then the CTA
+//   1. ranks:   rank = atomicAdd(arrivals[dest], 1)                          | barrier
+//   2. places:  q = staged[dest] + rank; the first line is completed in shared memory, entries
+//               of further complete lines (rare) go straight out, the remainder waits;
+//               lists the destinations that have a complete line             | barrier
+//   3. flushes: complete first lines, 2^line_shift lanes per line            | barrier
+//   4. restages the remainders at the front of their line, updates the books | barrier
+// A fragment is [dest][cta][frag_cap] as pass B expects; what does not fit a fragment (skew: one
+// k-mer flooding its partition) goes to the spill list exactly as before.
+#pragma once
+#include "consume.cuh"
+
+namespace oxg {
+
+constexpr int kScatThreads = 768;
+constexpr int kScatWarps = kScatThreads / 32;
+
+// per-warp tile buffers: forward bytes, mirrored complement, bad bits, end bits
+template <int K>
+struct ScatWarpBuf {
+    static constexpr int BL = TileGeom<K>::BL;
+    static constexpr int kBytes = 2 * BL + 64 + 64;
+};
+
+template <int K>
+inline size_t scatter_smem_bytes(uint32_t n_dest, uint32_t line_shift) {
+    return (size_t)n_dest * ((8u << line_shift) + 16) + 16 + (size_t)kScatWarps * ScatWarpBuf<K>::kBytes;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kScatThreads, 1) scatter_kernel(const ConsumeParams p) {
+    using G = TileGeom<K>;
+    constexpr int BL = G::BL, NV = G::NV, NE = G::NE;
+    static_assert(NV + 8 <= 32 && NE <= 16, "per-warp mask buffers are 64 bytes each");
+    extern __shared__ __align__(128) uint8_t sm[];
+    const uint32_t nd = p.n_dest, ls = p.line_shift, line = 1u << ls;
+    uint64_t *stage = reinterpret_cast<uint64_t *>(sm);                       // [nd][line]
+    uint32_t *arrivals = reinterpret_cast<uint32_t *>(sm + ((size_t)nd << (ls + 3)));  // [nd] this round
+    uint32_t *staged = arrivals + nd;                                         // [nd] entries waiting in the line (< line)
+    uint32_t *gpos = staged + nd;                                             // [nd] entries already in the fragment
+    uint32_t *flist = gpos + nd;                                              // [nd] destinations to flush this round
+    uint32_t *s_nflush = flist + nd;                                          // [4]
+    uint8_t *wbuf = reinterpret_cast<uint8_t *>(s_nflush + 4) + (size_t)(threadIdx.x >> 5) * ScatWarpBuf<K>::kBytes;
+    uint8_t *s_fw = wbuf, *s_rc = wbuf + BL;
+    uint16_t *s_bad = reinterpret_cast<uint16_t *>(wbuf + 2 * BL);
+    uint32_t *s_end = reinterpret_cast<uint32_t *>(wbuf + 2 * BL + 64);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < nd; i += kScatThreads) { arrivals[i] = 0; staged[i] = 0; gpos[i] = 0; }
+    if (threadIdx.x == 0) *s_nflush = 0;
+    __syncthreads();
+
+    const uint64_t frag_row = (uint64_t)gridDim.x * p.frag_cap;              // entries between destinations
+    uint64_t *const my_frag = p.frag + (uint64_t)blockIdx.x * p.frag_cap;    // + dest * frag_row
+    auto dest_of = [&](uint64_t h) {
+        uint32_t d = (uint32_t)((h * kPhi) >> p.part_shift);
+        if (p.n_ranks > 1) d += (uint32_t)(h >> p.owner_shift) * p.n_parts;
+        return d;
+    };
+    // what a destination takes this round and how much of it leaves as complete lines
+    auto books = [&](uint32_t d, uint32_t &total, uint32_t &full) {
+        total = min(staged[d] + arrivals[d], p.frag_cap - gpos[d]);
+        full = total & ~(line - 1);
+    };
+
+    uint64_t n_counted = 0, first_bad_unused = ~0ULL;
+    const uint64_t tiles_per_round = (uint64_t)gridDim.x * kScatWarps;
+    const uint64_t n_rounds = (p.n_tiles + tiles_per_round - 1) / tiles_per_round;
+    for (uint64_t r = 0; r < n_rounds; ++r) {
+        const uint64_t t = (r * gridDim.x + blockIdx.x) * kScatWarps + warp;
+        uint64_t h[kWPT] = {};
+        if (t < p.n_tiles) {
+            const uint64_t w0 = p.tile_base + t * kWarpTile;
+            const uint64_t tf = __ldg(p.tile_first + t);
+            const uint64_t rr = tf + lane;
+            const uint64_t off = rr < p.n_off ? __ldg(p.offsets + rr) : ~0ULL;
+            if (lane < NE) s_end[lane] = 0;
+            __syncwarp();
+            if (lane < NV) stage16<BL>(p, w0, lane, s_fw, s_rc, s_bad);
+            {
+                const uint64_t e = off - 1 - w0;  // last base of a read, tile-relative (sentinel: huge)
+                if (e < (uint64_t)BL) atomicOr(&s_end[e >> 5], 1u << (e & 31));
+                if (__shfl_sync(0xffffffffu, e < (uint64_t)BL, 31)) {
+                    // more than 32 read boundaries inside one tile (tiny or empty reads): walk the rest
+                    for (uint64_t q = tf + 32 + lane; q < p.n_off; q += 32) {
+                        const uint64_t e2 = p.offsets[q] - 1 - w0;
+                        if (e2 >= (uint64_t)BL) break;
+                        atomicOr(&s_end[e2 >> 5], 1u << (e2 & 31));
+                    }
+                }
+            }
+            __syncwarp();
+            const uint32_t valid = lane_valid_mask<K, kModePart>(p, s_bad, s_end, w0, lane, first_bad_unused);
+            if (valid) lane_hashes<K>(s_fw, s_rc, lane * kWPT, valid, h);
+        }
+
+        // 1. rank every hash inside its destination's arrivals of this round
+        uint32_t rank[kWPT];
+#pragma unroll
+        for (int j = 0; j < kWPT; ++j) {
+            rank[j] = 0;
+            if (h[j] != 0) { ++n_counted; rank[j] = atomicAdd(&arrivals[dest_of(h[j])], 1u); }
+        }
+        __syncthreads();
+
+        // 2. place; list the destinations whose first line is complete
+        uint32_t later = 0, spilled = 0;
+#pragma unroll
+        for (int j = 0; j < kWPT; ++j) {
+            if (h[j] == 0) continue;
+            const uint32_t d = dest_of(h[j]);
+            uint32_t total, full;
+            books(d, total, full);
+            const uint32_t q = staged[d] + rank[j];
+            if (q >= total) spilled |= 1u << j;                                  // the fragment is full
+            else if (q < line) stage[((size_t)d << ls) + q] = h[j];              // into the first line
+            else if (q < full) my_frag[d * frag_row + gpos[d] + q] = h[j];       // a further complete line: straight out
+            else { later |= 1u << j; rank[j] = q - full; }                       // remainder: restaged in step 4
+        }
+        for (uint32_t d = threadIdx.x; d < ((nd + 31) & ~31u); d += kScatThreads) {
+            uint32_t total = 0, full = 0;
+            if (d < nd) books(d, total, full);
+            const unsigned m = __ballot_sync(0xffffffffu, full != 0);
+            uint32_t base = 0;
+            if (lane == 0 && m) base = atomicAdd(s_nflush, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (full != 0) flist[base + __popc(m & ((1u << lane) - 1))] = d;
+        }
+        if (__any_sync(0xffffffffu, spilled != 0)) {
+            // skewed input (one k-mer flooding its partition): one reservation per warp tile
+            const uint32_t mine = __popc(spilled);
+            uint32_t incl = mine;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(p.spill_n, (unsigned long long)total);
+            base = __shfl_sync(0xffffffffu, base, 0) + (incl - mine);
+#pragma unroll
+            for (int j = 0; j < kWPT; ++j)
+                if ((spilled >> j) & 1u) { if (base < p.spill_cap) p.spill[base] = h[j]; ++base; }
+        }
+        __syncthreads();
+
+        // 3. flush the complete first lines: `line` consecutive lanes write one line
+        {
+            const uint32_t n_flush = *s_nflush;
+            const uint32_t per_warp = 32u >> ls, sub = lane >> ls, li = lane & (line - 1);
+            for (uint32_t e = warp * per_warp + sub; e < n_flush; e += kScatWarps * per_warp) {
+                const uint32_t d = flist[e];
+                my_frag[d * frag_row + gpos[d] + li] = stage[((size_t)d << ls) + li];
+            }
+        }
+        __syncthreads();
+
+        // 4. remainders to the front of their line; books for the next round
+#pragma unroll
+        for (int j = 0; j < kWPT; ++j)
+            if ((later >> j) & 1u) stage[((size_t)dest_of(h[j]) << ls) + rank[j]] = h[j];
+        for (uint32_t d = threadIdx.x; d < nd; d += kScatThreads) {
+            uint32_t total, full;
+            books(d, total, full);
+            gpos[d] += full;
+            staged[d] = total - full;
+            arrivals[d] = 0;
+        }
+        if (threadIdx.x == 0) *s_nflush = 0;
+        __syncthreads();
+    }
+
+    // what is still staged: partial lines, once per launch
+    for (uint32_t d = threadIdx.x; d < nd; d += kScatThreads) {
+        const uint32_t f = staged[d], g = gpos[d];
+        for (uint32_t i = 0; i < f; ++i) my_frag[d * frag_row + g + i] = stage[((size_t)d << ls) + i];
+        p.frag_cnt[(uint64_t)d * gridDim.x + blockIdx.x] = g + f;
+    }
+    for (int o = 16; o; o >>= 1) n_counted += __shfl_xor_sync(0xffffffffu, n_counted, o);
+    if (lane == 0 && n_counted) atomicAdd((unsigned long long *)&p.table.ctrl->counted, (unsigned long long)n_counted);
+}
+
+}  // namespace oxg

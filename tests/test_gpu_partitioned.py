@@ -51,7 +51,7 @@ def test_ragged_batch_skip_mode(capi, part, k):
     assert_same_table(t, ora)
 
 
-@pytest.mark.parametrize("n_parts,groups", [(2, 1), (64, 1), (1024, 1), (4096, 1), (256, 4), (8192, 3)])
+@pytest.mark.parametrize("n_parts,groups", [(2, 1), (64, 1), (1024, 1), (2048, 1), (4096, 1), (256, 4), (8192, 3)])
 def test_every_partition_geometry(capi, part, n_parts, groups):
     part(n_parts, groups)
     bases = synth_reads(30_000, 150, 200_000, seed=7, sub_ppm=10_000, n_ppm=1_000)
