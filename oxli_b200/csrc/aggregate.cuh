@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
             for (int u = 0; u < U; ++u) {
                 const uint32_t i = off + u * 32 + lane;
                 h[u] = i < n ? __ldcs(ptr + i) : 0;
-                bool ok = i < n;
+                bool ok = i < n && h[u] != 0;  // (0 pads the last line a launch of pass A wrote)
                 if (filter_owner && p.n_ranks > 1 && ok) ok = (int)(h[u] >> p.owner_shift) == p.self_rank;
                 live |= (ok ? 1u : 0u) << u;
             }

@@ -33,6 +33,12 @@ using namespace oxg;
 
 namespace {
 
+// Shards of one process wait for each other inside kernels on different streams; streams that
+// share a hardware work queue would serialise a wait in front of the kernel it waits for.  The
+// driver reads this when the context is created, so it is set when the library is loaded
+// (never overriding the user's choice).
+const int g_connections_set = setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 
@@ -86,6 +92,9 @@ static std::atomic<int> g_pipeline{[] {
     return e && !strcmp(e, "fused") ? 1 : e && !strcmp(e, "part") ? 2 : 0;
 }()};
 static std::atomic<uint32_t> g_parts_override{(uint32_t)env_int("OXLI_B200_PARTS", 0)};    // 0 = from the table size
+// pass A launches whose fragments pass B takes together (more duplicates per key meet in one
+// aggregation, one merge instead of several); 1 = pass B after every pass A
+static std::atomic<uint32_t> g_accumulate{(uint32_t)std::max(1, std::min(16, env_int("OXLI_B200_ACCUMULATE", 4)))};
 static std::atomic<uint32_t> g_groups_override{(uint32_t)env_int("OXLI_B200_GROUPS", 0)};  // 0 = default
 constexpr int kStageBufs = 4;  // host batches: chunks in flight between the copy stream and the kernels
 
@@ -102,6 +111,7 @@ struct DeviceCtx {
     uint64_t *h_offs[kStageBufs] = {};
     uint64_t offs_cap[kStageBufs] = {};
     cudaEvent_t ev_ready[kStageBufs] = {};
+    cudaEvent_t ev_stage_free[kStageBufs] = {};  // the kernels reading staging buffer b have finished
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_mid = nullptr;
     cudaEvent_t ev_user0 = nullptr, ev_user1 = nullptr;
     // scratch
@@ -146,7 +156,10 @@ oxg_status get_ctx(int dev, DeviceCtx **out) {
         c->sms = prop.multiProcessorCount;
         CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
-        for (int i = 0; i < kStageBufs; ++i) CU(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
+        for (int i = 0; i < kStageBufs; ++i) {
+            CU(cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->ev_stage_free[i], cudaEventDisableTiming));
+        }
         CU(cudaEventCreate(&c->ev_t0));
         CU(cudaEventCreate(&c->ev_t1));
         CU(cudaEventCreate(&c->ev_mid));
@@ -215,6 +228,21 @@ uint64_t capacity_for_keys(uint64_t keys) {
 
 }  // namespace
 
+namespace {
+struct PartPlan {
+    uint32_t n_parts = 0, part_bits = 0;   // partitions of one rank's table
+    int n_ranks = 1, self_rank = 0, owner_shift = 64;
+    uint32_t grid_a = 0;                   // CTAs of pass A = fragments per destination
+    uint32_t frag_cap = 0;                 // entries per fragment (multiple of the line)
+    uint32_t line_shift = 4;               // entries staged per destination before a line is written: 2^line_shift
+    uint64_t spill_cap = 0;
+    uint32_t groups = 1;
+    uint32_t n_dest() const { return n_parts * (uint32_t)n_ranks; }
+    uint64_t frag_entries() const { return (uint64_t)n_dest() * grid_a * frag_cap; }
+};
+
+}  // namespace
+
 struct oxg_table {
     DeviceCtx *ctx = nullptr;
     uint32_t k = 0;
@@ -228,6 +256,14 @@ struct oxg_table {
     bool pooled = false;     // slot arrays come from the stream-ordered allocator (shards: no call of
                              // theirs may synchronise the device while a peer's flag wait is running)
     float last_ms_a = 0.f, last_ms_b = 0.f;  // partitioned pipeline: pass A / pass B share of last_ms
+    // partitioned pipeline: pass A launches whose fragments are waiting for their pass B
+    struct {
+        bool active = false;
+        PartPlan pl;
+        uint32_t launches = 0;
+        uint64_t windows = 0, planned = 0;
+    } pend;
+    uint64_t part_budget = 0;  // windows the running consume call still has to go (0 = unknown)
     uint64_t last_new = 0;   // keys created by the previous consume launch (growth look-ahead)
     float last_ms = 0.f;
     uint64_t last_launches = 0;
@@ -384,18 +420,6 @@ oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
 
 // ---- partitioned pipeline: pass A (hash + scatter) and pass B (aggregate + merge) -----------
 
-struct PartPlan {
-    uint32_t n_parts = 0, part_bits = 0;   // partitions of one rank's table
-    int n_ranks = 1, self_rank = 0, owner_shift = 64;
-    uint32_t grid_a = 0;                   // CTAs of pass A = fragments per destination
-    uint32_t frag_cap = 0;                 // entries per fragment (multiple of the line)
-    uint32_t line_shift = 4;               // entries staged per destination before a line is written: 2^line_shift
-    uint64_t spill_cap = 0;
-    uint32_t groups = 1;
-    uint32_t n_dest() const { return n_parts * (uint32_t)n_ranks; }
-    uint64_t frag_entries() const { return (uint64_t)n_dest() * grid_a * frag_cap; }
-};
-
 bool use_partitioned(const oxg_table *t, uint64_t span) {
     if (!specialised_entry(t->k, kModePart)) return false;
     const int choice = g_pipeline.load();
@@ -421,7 +445,7 @@ uint32_t choose_parts(const oxg_table *t, uint32_t max_parts) {
 size_t scatter_smem_rt(uint32_t k, uint32_t n_dest, uint32_t line_shift) {
     const uint32_t q = 8 * ((k + 7 + 7) / 8);
     const uint32_t bl = ((kWarpTile - 8 + q) + 15) / 16 * 16;
-    return (size_t)n_dest * ((8u << line_shift) + 16) + 16 + (size_t)kScatWarps * (2 * bl + 128);
+    return (((size_t)n_dest * ((8u << line_shift) + 12) + 16 + 15) & ~(size_t)15) + (size_t)kScatWarps * (2 * bl + 128);
 }
 
 oxg_status plan_partitioned(oxg_table *t, uint64_t span, uint64_t n_tiles, int n_ranks, int self_rank, PartPlan *out) {
@@ -476,7 +500,7 @@ oxg_status ensure_part_buffers(DeviceCtx *c, const PartPlan &pl) {
 
 // pass A: p is a filled-in ConsumeParams (table.ctrl is where `counted` goes)
 oxg_status launch_part_a(oxg_table *t, ConsumeParams p, const PartPlan &pl, uint64_t *d_frag, uint32_t *d_frag_cnt,
-                         uint64_t *d_spill, unsigned long long *d_spill_n, cudaStream_t stream) {
+                         uint64_t *d_spill, unsigned long long *d_spill_n, cudaStream_t stream, bool append = false) {
     DeviceCtx *c = t->ctx;
     const void *fn = specialised_entry(t->k, kModePart);
     TRY(scatter_attr(c, t->k));
@@ -485,7 +509,8 @@ oxg_status launch_part_a(oxg_table *t, ConsumeParams p, const PartPlan &pl, uint
     p.n_parts = pl.n_parts; p.part_shift = 64 - pl.part_bits; p.n_dest = pl.n_dest(); p.line_shift = pl.line_shift;
     p.n_ranks = pl.n_ranks; p.self_rank = pl.self_rank; p.owner_shift = pl.owner_shift;
     p.spill = d_spill; p.spill_cap = pl.spill_cap; p.spill_n = d_spill_n;
-    CU(cudaMemsetAsync(d_spill_n, 0, 8, stream));
+    p.frag_append = append ? 1u : 0u;
+    if (!append) CU(cudaMemsetAsync(d_spill_n, 0, 8, stream));
     void *args[] = {&p};
     CU(cudaLaunchKernel(fn, dim3(pl.grid_a), dim3(kScatThreads), args, dyn, stream));
     LAUNCHED();
@@ -516,6 +541,31 @@ oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src,
     aggregate_kernel<<<grid, kAggThreads, smem, c->stream>>>(a);
     LAUNCHED();
     CU(cudaGetLastError());
+    return OXG_OK;
+}
+
+// pass B for the pass A launches accumulated so far, then the bookkeeping of a counting launch
+oxg_status flush_pending(oxg_table *t, uint64_t *counted) {
+    if (!t->pend.active) return OXG_OK;
+    DeviceCtx *c = t->ctx;
+    t->pend.active = false;
+    CU(cudaEventRecord(c->ev_mid, c->stream));
+    const AggSource own{c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n};
+    TRY(launch_part_b(t, t->pend.pl, &own, 1));
+    CU(cudaEventRecord(c->ev_t1, c->stream));
+    const uint64_t size_before = t->size;
+    TRY(pull_ctrl(t));
+    float ms = 0.f, ms_a = 0.f;
+    CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+    CU(cudaEventElapsedTime(&ms_a, c->ev_t0, c->ev_mid));
+    t->last_ms += ms; t->last_launches += t->pend.launches;
+    t->last_ms_a += ms_a; t->last_ms_b += ms - ms_a;
+    if (counted) *counted += t->h_ctrl->counted;
+    const uint64_t ov = t->h_ctrl->overflow;
+    // forecast for the next group: what this one created, unless the caller's hint still covers the table
+    const uint64_t made = t->size - size_before;
+    t->last_new = ov ? made + ov : (t->hinted && t->size <= t->hint_keys) ? 0 : made;
+    if (ov) TRY(drain_deferred(t, ov));
     return OXG_OK;
 }
 
@@ -550,8 +600,10 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
                 if (expect * 10 > t->cap * 7) TRY(grow_to_fit(t, expect));
                 else if (over_loaded(t->size, t->cap)) TRY(grow_to_fit(t, t->size));
             }
-            TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, span));
-            TRY(zero_ctrl_fields(t, kFieldCounted, kLaunchFields));  // counted, overflow, absorbed, tile and absorb counters
+            TRY(ensure_dev(&c->d_overflow, &c->overflow_cap, std::max<uint64_t>(span, t->pend.active ? t->pend.planned : 0)));
+            // counted, overflow, absorbed, tile and absorb counters -- unless a group of pass A
+            // launches is accumulating into them
+            if (!t->pend.active) TRY(zero_ctrl_fields(t, kFieldCounted, kLaunchFields));
         } else {
             TRY(zero_ctrl_fields(t, kFieldTile, 1));
         }
@@ -564,18 +616,26 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
         LAUNCHED();
         CU(cudaGetLastError());
         const bool part = mode == kModeCount && use_partitioned(t, hi - lo);
-        PartPlan pl;
         if (part) {
-            TRY(plan_partitioned(t, hi - lo, n_tiles, 1, 0, &pl));
-            TRY(ensure_part_buffers(c, pl));
+            // pass A now; pass B once the group of launches is complete (flush_pending)
+            const uint64_t span = hi - lo;
+            if (t->pend.active && t->pend.windows + span > t->pend.planned) TRY(flush_pending(t, counted));
+            if (!t->pend.active) {
+                const uint64_t planned = std::min<uint64_t>(std::max<uint64_t>(t->part_budget, span), (uint64_t)g_accumulate.load() * kLaunchWindows);
+                TRY(plan_partitioned(t, planned, planned / tw + 1, 1, 0, &t->pend.pl));
+                TRY(ensure_part_buffers(c, t->pend.pl));
+                t->pend.active = true; t->pend.launches = 0; t->pend.windows = 0; t->pend.planned = planned;
+                CU(cudaEventRecord(c->ev_t0, c->stream));
+            }
+            TRY(launch_part_a(t, p, t->pend.pl, c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n, c->stream, t->pend.launches > 0));
+            t->pend.launches += 1; t->pend.windows += span;
+            t->part_budget = t->part_budget > span ? t->part_budget - span : 0;
+            if (t->pend.launches >= g_accumulate.load() || t->pend.windows >= t->pend.planned) TRY(flush_pending(t, counted));
+            lo = hi;
+            continue;
         }
         CU(cudaEventRecord(c->ev_t0, c->stream));
-        if (part) {
-            TRY(launch_part_a(t, p, pl, c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n, c->stream));
-            CU(cudaEventRecord(c->ev_mid, c->stream));
-            const AggSource own{c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n};
-            TRY(launch_part_b(t, pl, &own, 1));
-        } else if (mode == kModeCount) TRY(launch_consume<kModeCount>(t, p));
+        if (mode == kModeCount) TRY(launch_consume<kModeCount>(t, p));
         else if (mode == kModeHash) TRY(launch_consume<kModeHash>(t, p));
         else TRY(launch_consume<kModeFirstBad>(t, p));
         CU(cudaEventRecord(c->ev_t1, c->stream));
@@ -585,14 +645,6 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
             float ms = 0.f;
             CU(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
             t->last_ms += ms; t->last_launches += 1;
-            if (part) {
-                float ms_a = 0.f;
-                CU(cudaEventElapsedTime(&ms_a, c->ev_t0, c->ev_mid));
-                t->last_ms_a += ms_a; t->last_ms_b += ms - ms_a;
-                // no look-ahead counter here: what this launch created is the forecast for the
-                // next one, unless the caller's hint still covers the table
-                t->h_ctrl->late_new = (t->hinted && t->size <= t->hint_keys) ? 0 : (t->size - size_before) / 4;
-            }
             if (counted) *counted += t->h_ctrl->counted;
             uint64_t ov = t->h_ctrl->overflow;
             // what the next launch of this stream will probably create: the rate of the last
@@ -619,6 +671,7 @@ oxg_status consume_resident(oxg_table *t, const uint8_t *d_bases, const uint64_t
     if (err_pos) *err_pos = 0;
     t->last_ms = 0.f; t->last_ms_a = 0.f; t->last_ms_b = 0.f; t->last_launches = 0;
     const uint64_t n_win = total >= k ? total - k + 1 : 0;
+    t->part_budget = n_win;
     oxg_status ret = OXG_OK;
     if (skip_bad || n_win == 0) {
         TRY(run_span(t, kModeCount, d_bases, 0, 0, n_win, total, d_offsets, n_reads + 1, nullptr, &counted));
@@ -644,13 +697,17 @@ oxg_status consume_resident(oxg_table *t, const uint8_t *d_bases, const uint64_t
             uint64_t in_read = 0;
             // everything before that read, then the clean prefix of the read itself
             TRY(run_span(t, kModeCount, d_bases, 0, 0, r_start >= k ? r_start - k + 1 : 0, r_start, d_offsets, n_reads + 1, nullptr, &counted));
+            TRY(flush_pending(t, &counted));  // the position reported below counts the windows of the bad read only
             TRY(run_span(t, kModeCount, d_bases, 0, r_start, fb, fb + k - 1, d_offsets, n_reads + 1, nullptr, &in_read));
+            TRY(flush_pending(t, &in_read));
             counted += in_read;
             if (err_read) *err_read = (int64_t)r;
             if (err_pos) *err_pos = in_read;
             ret = fail(OXG_ERR_BAD_KMER, "bad k-mer encountered at position %llu", (unsigned long long)in_read);
         }
     }
+    if (ret == OXG_OK) TRY(flush_pending(t, &counted));
+    t->part_budget = 0;
     if (total_counted) *total_counted = counted;
     return ret;
 }
@@ -889,6 +946,13 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
         for (uint64_t r = n_reads * ci / n_chunks, e = n_reads * (ci + 1) / n_chunks; r < e; ++r)
             if (offsets[r + 1] < offsets[r]) return fail(OXG_ERR_INVALID, "offsets must be non-decreasing");
         const Slice s = slice_of(ci);
+        if (ci >= (uint64_t)kStageBufs) {
+            // the buffer's previous chunk: its copy out of the pinned staging has finished (host
+            // side may be refilled) and its kernels have read the device side (a partitioned
+            // launch is only queued when run_span returns)
+            CU(cudaEventSynchronize(c->ev_ready[b]));
+            CU(cudaStreamWaitEvent(c->copy, c->ev_stage_free[b], 0));
+        }
         if (c->offs_cap[b] < s.n_off + 1) {
             CU(cudaStreamSynchronize(c->copy));
             if (c->d_offs[b]) CU(cudaFree(c->d_offs[b]));
@@ -912,8 +976,10 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
         const int b = (int)(ci % kStageBufs);
         const Slice s = slice_of(ci);
         CU(cudaStreamWaitEvent(c->stream, c->ev_ready[b], 0));
-        return run_span(t, mode, mapped ? mapped + base0 + s.lo : c->d_stage[b], s.lo, std::max(s.lo, w_lo),
-                        std::min(w_hi, s.lo + kChunkBytes), s.hi, c->d_offs[b], s.n_off + 1, nullptr, counted);
+        TRY(run_span(t, mode, mapped ? mapped + base0 + s.lo : c->d_stage[b], s.lo, std::max(s.lo, w_lo),
+                     std::min(w_hi, s.lo + kChunkBytes), s.hi, c->d_offs[b], s.n_off + 1, nullptr, counted));
+        CU(cudaEventRecord(c->ev_stage_free[b], c->stream));
+        return OXG_OK;
     };
     if (n_chunks == 1) {
         TRY(issue_copy(0));
@@ -1006,6 +1072,7 @@ oxg_status oxg_consume_batch(oxg_table *t, const uint8_t *bases, const uint64_t 
     const uint64_t n_win = total >= k ? total - k + 1 : 0;
     t->last_ms = 0.f; t->last_ms_a = 0.f; t->last_ms_b = 0.f; t->last_launches = 0;
     if (n_win == 0) return OXG_OK;
+    t->part_budget = n_win;
     cudaPointerAttributes attr{};
     bool pinned = cudaPointerGetAttributes(&attr, bases) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
@@ -1030,13 +1097,17 @@ oxg_status oxg_consume_batch(oxg_table *t, const uint8_t *bases, const uint64_t 
             const uint64_t r_start = offsets[r] - base0;
             uint64_t in_read = 0;
             TRY(stream_span(t, kModeCount, bases, offsets, n_reads, 0, r_start >= k ? r_start - k + 1 : 0, r_start, pinned, &counted));
+            TRY(flush_pending(t, &counted));  // the position reported below counts the windows of the bad read only
             TRY(stream_span(t, kModeCount, bases, offsets, n_reads, r_start, fb, fb + k - 1, pinned, &in_read));
+            TRY(flush_pending(t, &in_read));
             counted += in_read;
             if (err_read) *err_read = (int64_t)r;
             if (err_pos) *err_pos = in_read;
             ret = fail(OXG_ERR_BAD_KMER, "bad k-mer encountered at position %llu", (unsigned long long)in_read);
         }
     }
+    if (ret == OXG_OK) TRY(flush_pending(t, &counted));
+    t->part_budget = 0;
     if (total_counted) *total_counted = counted;
     return ret;
 }

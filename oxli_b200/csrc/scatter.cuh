@@ -17,11 +17,16 @@
 // One CTA of 24 warps per SM works in rounds: every warp hashes one tile of 256 window starts
 // (8 per lane), then the CTA
 //   1. ranks:   rank = atomicAdd(arrivals[dest], 1)                          | barrier
-//   2. places:  q = staged[dest] + rank; the first line is completed in shared memory, entries
-//               of further complete lines (rare) go straight out, the remainder waits;
+//   2. places:  q = accepted[dest] + rank is the hash's position in the fragment; the line being
+//               completed is filled in shared memory, entries of further complete lines (rare)
+//               go straight out, what lies beyond the last complete line waits;
 //               lists the destinations that have a complete line             | barrier
-//   3. flushes: complete first lines, 2^line_shift lanes per line            | barrier
-//   4. restages the remainders at the front of their line, updates the books | barrier
+//   3. flushes: completed lines, 2^line_shift lanes per line                 | barrier
+//   4. moves the waiting entries in at the front of their line, updates the books | barrier
+// At the end of a launch the last line of every destination goes out padded with zeros (0 is
+// never a hash here, src/lib.rs:589), so fill counts stay multiples of the line and a later
+// launch can continue the same fragments (frag_append): pass B then runs once per several
+// launches and sees more duplicates per key.
 // A fragment is [dest][cta][frag_cap] as pass B expects; what does not fit a fragment (skew: one
 // k-mer flooding its partition) goes to the spill list exactly as before.
 #pragma once
@@ -41,7 +46,7 @@ struct ScatWarpBuf {
 
 template <int K>
 inline size_t scatter_smem_bytes(uint32_t n_dest, uint32_t line_shift) {
-    return (size_t)n_dest * ((8u << line_shift) + 16) + 16 + (size_t)kScatWarps * ScatWarpBuf<K>::kBytes;
+    return (((size_t)n_dest * ((8u << line_shift) + 12) + 16 + 15) & ~(size_t)15) + (size_t)kScatWarps * ScatWarpBuf<K>::kBytes;
 }
 
 template <int K>
@@ -52,48 +57,65 @@ __global__ void __launch_bounds__(kScatThreads, 1) scatter_kernel(const ConsumeP
     extern __shared__ __align__(128) uint8_t sm[];
     const uint32_t nd = p.n_dest, ls = p.line_shift, line = 1u << ls;
     uint64_t *stage = reinterpret_cast<uint64_t *>(sm);                       // [nd][line]
-    uint32_t *arrivals = reinterpret_cast<uint32_t *>(sm + ((size_t)nd << (ls + 3)));  // [nd] this round
-    uint32_t *staged = arrivals + nd;                                         // [nd] entries waiting in the line (< line)
-    uint32_t *gpos = staged + nd;                                             // [nd] entries already in the fragment
-    uint32_t *flist = gpos + nd;                                              // [nd] destinations to flush this round
+    // book[d] = {entries accepted so far (in the fragment or staged), arrivals of this round}
+    uint2 *book = reinterpret_cast<uint2 *>(sm + ((size_t)nd << (ls + 3)));  // [nd]
+    uint32_t *flist = reinterpret_cast<uint32_t *>(book + nd);                // [nd] destinations to flush this round
     uint32_t *s_nflush = flist + nd;                                          // [4]
-    uint8_t *wbuf = reinterpret_cast<uint8_t *>(s_nflush + 4) + (size_t)(threadIdx.x >> 5) * ScatWarpBuf<K>::kBytes;
+    uint8_t *wbuf = sm + ((((size_t)nd * ((8u << ls) + 12) + 16) + 15) & ~(size_t)15) + (size_t)(threadIdx.x >> 5) * ScatWarpBuf<K>::kBytes;
     uint8_t *s_fw = wbuf, *s_rc = wbuf + BL;
     uint16_t *s_bad = reinterpret_cast<uint16_t *>(wbuf + 2 * BL);
     uint32_t *s_end = reinterpret_cast<uint32_t *>(wbuf + 2 * BL + 64);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < nd; i += kScatThreads) { arrivals[i] = 0; staged[i] = 0; gpos[i] = 0; }
+    const uint64_t frag_row = (uint64_t)gridDim.x * p.frag_cap;              // entries between destinations
+    uint64_t *const my_frag = p.frag + (uint64_t)blockIdx.x * p.frag_cap;    // + dest * frag_row
+    // a launch may continue fragments an earlier launch began (frag_append): their fill counts are
+    // multiples of the line, because every launch pads its last lines with zeros (pass B skips them)
+    for (uint32_t i = threadIdx.x; i < nd; i += kScatThreads)
+        book[i] = make_uint2(p.frag_append ? p.frag_cnt[(uint64_t)i * gridDim.x + blockIdx.x] : 0u, 0u);
+    for (uint32_t i = threadIdx.x; i < (nd << ls); i += kScatThreads) stage[i] = 0;
     if (threadIdx.x == 0) *s_nflush = 0;
     __syncthreads();
 
-    const uint64_t frag_row = (uint64_t)gridDim.x * p.frag_cap;              // entries between destinations
-    uint64_t *const my_frag = p.frag + (uint64_t)blockIdx.x * p.frag_cap;    // + dest * frag_row
     auto dest_of = [&](uint64_t h) {
         uint32_t d = (uint32_t)((h * kPhi) >> p.part_shift);
         if (p.n_ranks > 1) d += (uint32_t)(h >> p.owner_shift) * p.n_parts;
         return d;
     };
-    // what a destination takes this round and how much of it leaves as complete lines
-    auto books = [&](uint32_t d, uint32_t &total, uint32_t &full) {
-        total = min(staged[d] + arrivals[d], p.frag_cap - gpos[d]);
-        full = total & ~(line - 1);
-    };
 
     uint64_t n_counted = 0, first_bad_unused = ~0ULL;
     const uint64_t tiles_per_round = (uint64_t)gridDim.x * kScatWarps;
     const uint64_t n_rounds = (p.n_tiles + tiles_per_round - 1) / tiles_per_round;
+    auto tile_of = [&](uint64_t r) { return (r * gridDim.x + blockIdx.x) * kScatWarps + warp; };
+
+    // software pipeline over rounds: the bytes and read boundaries of the next tile are fetched
+    // into registers while this one is hashed and scattered
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    uint64_t tf = 0, off = ~0ULL;
+    auto fetch = [&](uint64_t t, uint4 &raw_, uint64_t &tf_) {
+        if (t < p.n_tiles) {
+            if (lane < NV) raw_ = load_bases16(p, p.tile_base + t * kWarpTile + 16ull * lane);
+            tf_ = __ldg(p.tile_first + t);
+        }
+    };
+    auto fetch_off = [&](uint64_t t, uint64_t tf_) {
+        const uint64_t rr = tf_ + lane;
+        return (t < p.n_tiles && rr < p.n_off) ? __ldg(p.offsets + rr) : ~0ULL;
+    };
+    fetch(tile_of(0), raw, tf);
+    off = fetch_off(tile_of(0), tf);
+
     for (uint64_t r = 0; r < n_rounds; ++r) {
-        const uint64_t t = (r * gridDim.x + blockIdx.x) * kScatWarps + warp;
+        const uint64_t t = tile_of(r);
+        uint4 raw_next = make_uint4(0, 0, 0, 0);
+        uint64_t tf_next = 0;
+        fetch(tile_of(r + 1), raw_next, tf_next);
         uint64_t h[kWPT] = {};
         if (t < p.n_tiles) {
             const uint64_t w0 = p.tile_base + t * kWarpTile;
-            const uint64_t tf = __ldg(p.tile_first + t);
-            const uint64_t rr = tf + lane;
-            const uint64_t off = rr < p.n_off ? __ldg(p.offsets + rr) : ~0ULL;
             if (lane < NE) s_end[lane] = 0;
             __syncwarp();
-            if (lane < NV) stage16<BL>(p, w0, lane, s_fw, s_rc, s_bad);
+            if (lane < NV) stage16_raw<BL>(p, w0, lane, raw, s_fw, s_rc, s_bad);
             {
                 const uint64_t e = off - 1 - w0;  // last base of a read, tile-relative (sentinel: huge)
                 if (e < (uint64_t)BL) atomicOr(&s_end[e >> 5], 1u << (e & 31));
@@ -110,38 +132,43 @@ __global__ void __launch_bounds__(kScatThreads, 1) scatter_kernel(const ConsumeP
             const uint32_t valid = lane_valid_mask<K, kModePart>(p, s_bad, s_end, w0, lane, first_bad_unused);
             if (valid) lane_hashes<K>(s_fw, s_rc, lane * kWPT, valid, h);
         }
+        const uint64_t off_next = fetch_off(tile_of(r + 1), tf_next);  // its tile_first entry has arrived by now
 
         // 1. rank every hash inside its destination's arrivals of this round
-        uint32_t rank[kWPT];
+        uint32_t dst[kWPT], rank[kWPT];
 #pragma unroll
         for (int j = 0; j < kWPT; ++j) {
-            rank[j] = 0;
-            if (h[j] != 0) { ++n_counted; rank[j] = atomicAdd(&arrivals[dest_of(h[j])], 1u); }
+            dst[j] = 0; rank[j] = 0;
+            if (h[j] != 0) { ++n_counted; dst[j] = dest_of(h[j]); rank[j] = atomicAdd(&book[dst[j]].y, 1u); }
         }
         __syncthreads();
 
-        // 2. place; list the destinations whose first line is complete
+        // 2. place: absolute position q in the fragment; the line being completed is filled in
+        //    shared memory, entries of further complete lines (rare) go straight out, what lies
+        //    beyond the last complete line waits for the flush.  List the destinations to flush.
         uint32_t later = 0, spilled = 0;
 #pragma unroll
         for (int j = 0; j < kWPT; ++j) {
             if (h[j] == 0) continue;
-            const uint32_t d = dest_of(h[j]);
-            uint32_t total, full;
-            books(d, total, full);
-            const uint32_t q = staged[d] + rank[j];
-            if (q >= total) spilled |= 1u << j;                                  // the fragment is full
-            else if (q < line) stage[((size_t)d << ls) + q] = h[j];              // into the first line
-            else if (q < full) my_frag[d * frag_row + gpos[d] + q] = h[j];       // a further complete line: straight out
-            else { later |= 1u << j; rank[j] = q - full; }                       // remainder: restaged in step 4
+            const uint2 b = book[dst[j]];
+            const uint32_t total = min(b.x + b.y, p.frag_cap), full = total & ~(line - 1);
+            const uint32_t q = b.x + rank[j];
+            if (q >= total) spilled |= 1u << j;                                        // the fragment is full
+            else if (q < (b.x & ~(line - 1)) + line) stage[((size_t)dst[j] << ls) + (q & (line - 1))] = h[j];
+            else if (q < full) my_frag[dst[j] * frag_row + q] = h[j];
+            else { later |= 1u << j; rank[j] = q; }
         }
         for (uint32_t d = threadIdx.x; d < ((nd + 31) & ~31u); d += kScatThreads) {
-            uint32_t total = 0, full = 0;
-            if (d < nd) books(d, total, full);
-            const unsigned m = __ballot_sync(0xffffffffu, full != 0);
+            bool flush = false;
+            if (d < nd) {
+                const uint2 b = book[d];
+                flush = min(b.x + b.y, p.frag_cap) >= (b.x & ~(line - 1)) + line;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, flush);
             uint32_t base = 0;
             if (lane == 0 && m) base = atomicAdd(s_nflush, (uint32_t)__popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (full != 0) flist[base + __popc(m & ((1u << lane) - 1))] = d;
+            if (flush) flist[base + __popc(m & ((1u << lane) - 1))] = d;
         }
         if (__any_sync(0xffffffffu, spilled != 0)) {
             // skewed input (one k-mer flooding its partition): one reservation per warp tile
@@ -151,9 +178,9 @@ __global__ void __launch_bounds__(kScatThreads, 1) scatter_kernel(const ConsumeP
                 const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += v;
             }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(p.spill_n, (unsigned long long)total);
+            if (lane == 0) base = atomicAdd(p.spill_n, (unsigned long long)tot);
             base = __shfl_sync(0xffffffffu, base, 0) + (incl - mine);
 #pragma unroll
             for (int j = 0; j < kWPT; ++j)
@@ -161,37 +188,41 @@ __global__ void __launch_bounds__(kScatThreads, 1) scatter_kernel(const ConsumeP
         }
         __syncthreads();
 
-        // 3. flush the complete first lines: `line` consecutive lanes write one line
+        // 3. flush the completed lines: `line` consecutive lanes write one line
         {
             const uint32_t n_flush = *s_nflush;
             const uint32_t per_warp = 32u >> ls, sub = lane >> ls, li = lane & (line - 1);
             for (uint32_t e = warp * per_warp + sub; e < n_flush; e += kScatWarps * per_warp) {
                 const uint32_t d = flist[e];
-                my_frag[d * frag_row + gpos[d] + li] = stage[((size_t)d << ls) + li];
+                my_frag[d * frag_row + (book[d].x & ~(line - 1)) + li] = stage[((size_t)d << ls) + li];
             }
         }
         __syncthreads();
 
-        // 4. remainders to the front of their line; books for the next round
+        // 4. what lies beyond the flushed lines moves in at the front of its line; the books
 #pragma unroll
         for (int j = 0; j < kWPT; ++j)
-            if ((later >> j) & 1u) stage[((size_t)dest_of(h[j]) << ls) + rank[j]] = h[j];
+            if ((later >> j) & 1u) stage[((size_t)dst[j] << ls) + (rank[j] & (line - 1))] = h[j];
         for (uint32_t d = threadIdx.x; d < nd; d += kScatThreads) {
-            uint32_t total, full;
-            books(d, total, full);
-            gpos[d] += full;
-            staged[d] = total - full;
-            arrivals[d] = 0;
+            const uint2 b = book[d];
+            book[d] = make_uint2(min(b.x + b.y, p.frag_cap), 0u);
         }
         if (threadIdx.x == 0) *s_nflush = 0;
         __syncthreads();
+        raw = raw_next; tf = tf_next; off = off_next;
     }
 
-    // what is still staged: partial lines, once per launch
-    for (uint32_t d = threadIdx.x; d < nd; d += kScatThreads) {
-        const uint32_t f = staged[d], g = gpos[d];
-        for (uint32_t i = 0; i < f; ++i) my_frag[d * frag_row + g + i] = stage[((size_t)d << ls) + i];
-        p.frag_cnt[(uint64_t)d * gridDim.x + blockIdx.x] = g + f;
+    // what is still staged: the last line of every destination goes out whole, its unused slots
+    // holding 0 (never a hash: pass A drops it, src/lib.rs:589) so that fill counts stay multiples
+    // of the line and a later launch can continue the fragment
+    {
+        const uint32_t per_warp = 32u >> ls, sub = lane >> ls, li = lane & (line - 1);
+        for (uint32_t d = warp * per_warp + sub; d < nd; d += kScatWarps * per_warp) {
+            const uint32_t pos = book[d].x, part = pos & (line - 1);
+            if (part) my_frag[d * frag_row + (pos - part) + li] = li < part ? stage[((size_t)d << ls) + li] : 0ull;
+        }
+        for (uint32_t d = threadIdx.x; d < nd; d += kScatThreads)
+            p.frag_cnt[(uint64_t)d * gridDim.x + blockIdx.x] = min((book[d].x + line - 1) & ~(line - 1), p.frag_cap);
     }
     for (int o = 16; o; o >>= 1) n_counted += __shfl_xor_sync(0xffffffffu, n_counted, o);
     if (lane == 0 && n_counted) atomicAdd((unsigned long long *)&p.table.ctrl->counted, (unsigned long long)n_counted);
