@@ -30,13 +30,14 @@
 
 namespace oxg {
 
-constexpr int kAggThreads = 512;
+constexpr int kAggThreads = 1024;                    // one CTA per SM
 constexpr int kAggWarps = kAggThreads / 32;
-constexpr int kLocalBits = 13;
-constexpr uint32_t kLocalSlots = 1u << kLocalBits;  // 8192 x (8-byte key + 4-byte count) = 96 KB
+constexpr int kLocalBits = 14;
+constexpr uint32_t kLocalSlots = 1u << kLocalBits;  // 16384 x (8-byte key + 4-byte count) = 192 KB
 constexpr int kLocalProbe = 4;                      // buckets of two slots examined before bypassing
-constexpr uint32_t kSpillSlice = 1u << 15;          // spill-list entries per work item
+constexpr uint32_t kSpillSlice = 1u << 16;          // spill-list entries per work item
 constexpr int kMaxSources = 16;
+constexpr uint32_t kAggMaxFrags = 296 * kMaxSources;  // fragments of one partition: pass A CTAs x sources
 
 struct AggSource {
     const uint64_t *frag;                 // [n_dest_total][n_ctas][frag_cap]
@@ -60,7 +61,7 @@ struct AggParams {
     unsigned long long *work_counter;     // zeroed before the launch
 };
 
-inline size_t aggregate_smem_bytes() { return (size_t)kLocalSlots * 12; }
+inline size_t aggregate_smem_bytes() { return (size_t)kLocalSlots * 12 + (size_t)kAggMaxFrags * 4; }
 
 // One occurrence of h into the shared-memory table.  false = neighbourhood full, bypass.
 // Slots only ever go from empty to a key, so a stale "empty" is caught by the CAS and a stale
@@ -85,14 +86,16 @@ __device__ __forceinline__ bool local_count(uint64_t *lk, uint32_t *ld, uint64_t
     return false;
 }
 
-__global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggParams p) {
+__global__ void __launch_bounds__(kAggThreads, 1) aggregate_kernel(const AggParams p) {
     extern __shared__ __align__(16) uint8_t agg_smem[];
     uint64_t *lk = reinterpret_cast<uint64_t *>(agg_smem);                    // keys
     uint32_t *ld = reinterpret_cast<uint32_t *>(agg_smem + kLocalSlots * 8);  // occurrences
+    uint32_t *s_cnt = ld + kLocalSlots;                                       // fill counts of the item's fragments
     __shared__ unsigned long long s_item;
+    __shared__ uint32_t s_next;                          // next fragment (or spill run) of the item to hand out
     __shared__ uint64_t s_spill_first[kMaxSources + 1];  // work-item index of each source's first spill slice
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const TableView &tv = p.table;
 
     if (threadIdx.x == 0) {
@@ -116,8 +119,9 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
     };
 
     // U hashes per lane: through the shared-memory table first; what bypasses it goes to the
-    // table in HBM with all home-bucket loads in flight together
+    // table in HBM with the home-bucket loads in flight together
     constexpr int U = 4;
+    constexpr uint32_t kBlk = 32 * U;  // hashes a warp takes per step
     auto take = [&](const uint64_t (&h)[U], uint32_t live, bool full) {
         uint32_t direct = 0;
 #pragma unroll
@@ -133,27 +137,29 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
             if (direct >> 2) created += table_add_many<2>(tv, hi2, one, direct >> 2, full);
         }
     };
-    // a contiguous run of n hashes, consumed by one warp
-    auto take_run = [&](const uint64_t *ptr, uint32_t n, bool filter_owner, bool full) {
-        for (uint32_t off = 0; off < n; off += 32 * U) {
-            uint64_t h[U];
-            uint32_t live = 0;
+    // the lanes' share of a block of n <= kBlk hashes at ptr
+    auto load_blk = [&](const uint64_t *ptr, uint32_t n, uint64_t (&h)[U]) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t i = off + u * 32 + lane;
-                h[u] = i < n ? __ldcs(ptr + i) : 0;
-                bool ok = i < n && h[u] != 0;  // (0 pads the last line a launch of pass A wrote)
-                if (filter_owner && p.n_ranks > 1 && ok) ok = (int)(h[u] >> p.owner_shift) == p.self_rank;
-                live |= (ok ? 1u : 0u) << u;
-            }
-            n_taken += __popc(live);
-            take(h, live, full);
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = u * 32 + lane;
+            h[u] = i < n ? __ldcs(ptr + i) : 0;
         }
+    };
+    auto take_blk = [&](const uint64_t (&h)[U], bool filter_owner, bool full) {
+        uint32_t live = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            bool ok = h[u] != 0;  // (0 pads the last line a launch of pass A wrote, and the block's tail)
+            if (filter_owner && p.n_ranks > 1 && ok) ok = (int)(h[u] >> p.owner_shift) == p.self_rank;
+            live |= (ok ? 1u : 0u) << u;
+        }
+        n_taken += __popc(live);
+        take(h, live, full);
     };
 
     for (;;) {
         __syncthreads();  // previous item fully merged; s_item free
-        if (threadIdx.x == 0) s_item = atomicAdd(p.work_counter, 1ULL);
+        if (threadIdx.x == 0) { s_item = atomicAdd(p.work_counter, 1ULL); s_next = 0; }
         // empty the cache
         for (uint32_t i = threadIdx.x; i < kLocalSlots / 2; i += kAggThreads)
             reinterpret_cast<ulonglong2 *>(lk)[i] = make_ulonglong2(kEmpty, kEmpty);
@@ -162,33 +168,47 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
         __syncthreads();
         const uint64_t item = s_item;
         if (item >= n_items) break;
+        const bool full = tv.overflow != nullptr && __ldcg(&tv.ctrl->size) >= tv.limit;
 
         if (item < (uint64_t)p.n_parts * p.groups) {
-            // a partition of this rank's table: its fragments from every source and pass-A CTA
-            // (with groups > 1, one share of them: neighbouring CTAs then work on the same
-            // segment of the table at the same time)
+            // A partition of this rank's table: its fragments from every source and pass-A CTA
+            // (with groups > 1, one share of them).  Fill counts first, all at once; then the
+            // warps take fragments as they come free, always one block of hashes ahead.
             const uint64_t dest = p.dest0 + item / p.groups;
             const uint32_t g = (uint32_t)(item % p.groups);
-            const uint32_t n_frag = p.n_ctas * (uint32_t)p.n_src;
-            const bool full = tv.overflow != nullptr && __ldcg(&tv.ctrl->size) >= tv.limit;
-            // warp w takes the fragments g + (w + kAggWarps * i) * groups; their fill counts are
-            // fetched 32 at a time, one per lane, so that a fragment costs no latency of its own
-            for (uint32_t f0 = g + warp * p.groups; f0 < n_frag; f0 += 32 * kAggWarps * p.groups) {
-                const uint32_t mine = f0 + lane * kAggWarps * p.groups;
-                uint32_t my_n = 0;
-                const uint64_t *my_ptr = nullptr;
-                if (mine < n_frag) {
-                    const int s = (int)(mine / p.n_ctas);
-                    const uint64_t row = dest * p.n_ctas + (mine - (uint32_t)s * p.n_ctas);
-                    my_n = min(__ldg(p.src[s].frag_cnt + row), p.frag_cap);
-                    my_ptr = p.src[s].frag + row * p.frag_cap;
+            const uint32_t n_frag = min(p.n_ctas * (uint32_t)p.n_src, kAggMaxFrags);
+            for (uint32_t f = threadIdx.x; f < n_frag; f += kAggThreads) {
+                const uint32_t s = f / p.n_ctas;
+                s_cnt[f] = min(__ldg(p.src[s].frag_cnt + dest * p.n_ctas + (f - s * p.n_ctas)), p.frag_cap);
+            }
+            __syncthreads();
+            const uint64_t *cur = nullptr;  // rest of the fragment in hand
+            uint32_t left = 0;
+            auto next_blk = [&](const uint64_t *&ptr, uint32_t &n) {  // warp-uniform; n = 0: nothing left
+                while (left == 0) {
+                    uint32_t f = 0;
+                    if (lane == 0) f = atomicAdd(&s_next, 1u);
+                    f = g + __shfl_sync(0xffffffffu, f, 0) * p.groups;
+                    if (f >= n_frag) { n = 0; return; }
+                    const uint32_t s = f / p.n_ctas;
+                    left = s_cnt[f];
+                    cur = p.src[s].frag + (dest * p.n_ctas + (f - s * p.n_ctas)) * p.frag_cap;
                 }
-                for (int l = 0; l < 32; ++l) {
-                    const uint32_t n = __shfl_sync(0xffffffffu, my_n, l);
-                    const uint64_t *ptr = reinterpret_cast<const uint64_t *>(__shfl_sync(0xffffffffu, (unsigned long long)my_ptr, l));
-                    if (f0 + (uint32_t)l * kAggWarps * p.groups >= n_frag) break;
-                    if (n) take_run(ptr, n, false, full);
-                }
+                ptr = cur; n = min(left, kBlk);
+                cur += n; left -= n;
+            };
+            const uint64_t *ptr = nullptr, *ptr2 = nullptr;
+            uint32_t n = 0, n2 = 0;
+            uint64_t h[U], h2[U];
+            next_blk(ptr, n);
+            if (n) load_blk(ptr, n, h);
+            while (n) {
+                next_blk(ptr2, n2);
+                if (n2) load_blk(ptr2, n2, h2);
+                take_blk(h, false, full);
+                n = n2;
+#pragma unroll
+                for (int u = 0; u < U; ++u) h[u] = h2[u];
             }
             flush_created();
         } else {
@@ -198,10 +218,16 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
             const uint64_t n_sp = min((uint64_t)*p.src[s].spill_n, p.spill_cap);
             const uint64_t lo = (item - s_spill_first[s]) * kSpillSlice;
             const uint64_t hi = min(n_sp, lo + kSpillSlice);
-            constexpr uint32_t kRun = kSpillSlice / kAggWarps;
-            const uint64_t a = lo + (uint64_t)warp * kRun;
-            const bool full = tv.overflow != nullptr && __ldcg(&tv.ctrl->size) >= tv.limit;
-            if (a < hi) take_run(p.src[s].spill + a, (uint32_t)min((uint64_t)kRun, hi - a), true, full);
+            for (;;) {
+                uint32_t b = 0;
+                if (lane == 0) b = atomicAdd(&s_next, 1u);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                const uint64_t at = lo + (uint64_t)b * kBlk;
+                if (at >= hi) break;
+                uint64_t h[U];
+                load_blk(p.src[s].spill + at, (uint32_t)min((uint64_t)kBlk, hi - at), h);
+                take_blk(h, true, full);
+            }
             flush_created();
         }
         __syncthreads();  // the cache holds every occurrence that did not bypass it
@@ -209,7 +235,6 @@ __global__ void __launch_bounds__(kAggThreads, 2) aggregate_kernel(const AggPara
         // merge: distinct keys of this item, in slot order of the table (the cache index is the
         // next-lower bits of the same product h * phi)
         {
-            const bool full = tv.overflow != nullptr && __ldcg(&tv.ctrl->size) >= tv.limit;
             constexpr int M = 2;
             for (uint32_t base = 0; base < kLocalSlots; base += kAggThreads * M) {
                 uint64_t key[M], inc[M];

@@ -433,7 +433,7 @@ bool use_partitioned(const oxg_table *t, uint64_t span) {
 // max_parts, because pass A stages one line per destination in shared memory.
 uint32_t choose_parts(const oxg_table *t, uint32_t max_parts) {
     const uint32_t forced = g_parts_override.load();
-    if (forced >= 2 && !(forced & (forced - 1))) return std::min(forced, std::max(max_parts * 4, 2u));  // (up to 4096 destinations, with shorter lines)
+    if (forced >= 2 && !(forced & (forced - 1))) return std::min(forced, std::max(max_parts * 2, 2u));  // (up to 2048 destinations, with shorter lines)
     const uint64_t est = std::max(t->size + t->last_new, t->hint_keys);
     if (est == 0) return std::min<uint32_t>(1024, max_parts);
     uint64_t parts = 64;
@@ -458,11 +458,13 @@ oxg_status plan_partitioned(oxg_table *t, uint64_t span, uint64_t n_tiles, int n
     int lg = 0;
     while ((1 << lg) < n_ranks) ++lg;
     pl.owner_shift = 64 - lg;
-    pl.line_shift = pl.n_dest() <= 1024 ? 4 : pl.n_dest() <= 2048 ? 3 : 2;
-    if (pl.n_dest() > 4096) return fail(OXG_ERR_INVALID, "internal: too many scatter destinations");
-    // one CTA per SM (its staging fills the SM's shared memory); fewer when the launch is small
+    // the staged line: as long as the shared memory of kScatCtasPerSm CTAs per SM allows
+    pl.line_shift = 4;
+    while (pl.line_shift > 1 && scatter_smem_rt(t->k, pl.n_dest(), pl.line_shift) * kScatCtasPerSm > 220u * 1024) --pl.line_shift;
+    if (scatter_smem_rt(t->k, pl.n_dest(), pl.line_shift) * kScatCtasPerSm > 220u * 1024) return fail(OXG_ERR_INVALID, "internal: too many scatter destinations");
+    // kScatCtasPerSm CTAs per SM (their staging fills the SM's shared memory); fewer when the launch is small
     const uint64_t tiles_per_cta = kScatWarps;
-    pl.grid_a = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n_tiles + tiles_per_cta - 1) / tiles_per_cta, (uint64_t)c->sms));
+    pl.grid_a = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((n_tiles + tiles_per_cta - 1) / tiles_per_cta, (uint64_t)c->sms * kScatCtasPerSm));
     // a fragment holds its fair share of the launch's windows plus half again plus four standard
     // deviations; what does not fit (skew) goes to the spill list, which can take the whole launch
     const uint64_t line = 1ull << pl.line_shift;
@@ -589,6 +591,9 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
         TRY(ensure_dev(&c->d_tile_first, &c->tile_first_cap, n_tiles));
         if (mode == kModeCount) {
             const uint64_t span = hi - lo;
+            // a launch that will not join the group of pass A launches in flight (too small for the
+            // partitioned pipeline) must not share its launch counters: complete the group first
+            if (t->pend.active && !use_partitioned(t, span)) TRY(flush_pending(t, counted));
             if (span <= kSmallBatch) TRY(reserve_keys(t, span));
             else {
                 // Look ahead instead of running into the load limit mid-launch: a table nobody

@@ -14,7 +14,7 @@
 // with one shared-memory atomic each and a line leaves the SM as ONE full-width coalesced
 // store when it is complete.
 //
-// One CTA of 24 warps per SM works in rounds: every warp hashes one tile of 256 window starts
+// A CTA of 12 warps (two per SM) works in rounds: every warp hashes one tile of 256 window starts
 // (8 per lane), then the CTA
 //   1. ranks:   rank = atomicAdd(arrivals[dest], 1)                          | barrier
 //   2. places:  q = accepted[dest] + rank is the hash's position in the fragment; the line being
@@ -34,7 +34,16 @@
 
 namespace oxg {
 
-constexpr int kScatThreads = 768;
+// Two CTAs of 12 warps per SM rather than one of 24: the phases between barriers are short and
+// serial in nature, and while one CTA is in them the other one hashes.
+#ifndef OXG_SCAT_THREADS
+#define OXG_SCAT_THREADS 384
+#endif
+#ifndef OXG_SCAT_CTAS
+#define OXG_SCAT_CTAS 2
+#endif
+constexpr int kScatThreads = OXG_SCAT_THREADS;
+constexpr int kScatCtasPerSm = OXG_SCAT_CTAS;
 constexpr int kScatWarps = kScatThreads / 32;
 
 // per-warp tile buffers: forward bytes, mirrored complement, bad bits, end bits
@@ -50,7 +59,7 @@ inline size_t scatter_smem_bytes(uint32_t n_dest, uint32_t line_shift) {
 }
 
 template <int K>
-__global__ void __launch_bounds__(kScatThreads, 1) scatter_kernel(const ConsumeParams p) {
+__global__ void __launch_bounds__(kScatThreads, kScatCtasPerSm) scatter_kernel(const ConsumeParams p) {
     using G = TileGeom<K>;
     constexpr int BL = G::BL, NV = G::NV, NE = G::NE;
     static_assert(NV + 8 <= 32 && NE <= 16, "per-warp mask buffers are 64 bytes each");
