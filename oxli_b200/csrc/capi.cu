@@ -520,12 +520,24 @@ oxg_status launch_part_a(oxg_table *t, ConsumeParams p, const PartPlan &pl, uint
     return OXG_OK;
 }
 
+// the aggregation kernel is built for three CTA sizes (one CTA per SM each); OXLI_B200_AGG_THREADS picks
+static const int g_agg_threads = [] { const int v = env_int("OXLI_B200_AGG_THREADS", kAggThreadsDefault); return v == 512 || v == 768 || v == 1024 ? v : kAggThreadsDefault; }();
+int agg_threads() { return g_agg_threads; }
+const void *agg_fn() {
+    return g_agg_threads == 512 ? (const void *)aggregate_kernel<512> : g_agg_threads == 1024 ? (const void *)aggregate_kernel<1024> : (const void *)aggregate_kernel<768>;
+}
+oxg_status launch_aggregate(const AggParams &a, int grid, size_t smem, cudaStream_t stream) {
+    void *args[] = {const_cast<AggParams *>(&a)};
+    CU(cudaLaunchKernel(agg_fn(), dim3(grid), dim3(g_agg_threads), args, smem, stream));
+    return OXG_OK;
+}
+
 // pass B over n_src sources (one, this device's own pass A output, without sharding)
 oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src, int n_src) {
     DeviceCtx *c = t->ctx;
     const size_t smem = aggregate_smem_bytes();
     if (!c->agg_attr_done) {
-        CU(cudaFuncSetAttribute((const void *)aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(agg_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         c->agg_attr_done = true;
     }
     AggParams a{};
@@ -537,10 +549,10 @@ oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src,
     a.owner_shift = pl.owner_shift; a.self_rank = pl.self_rank; a.n_ranks = pl.n_ranks;
     a.work_counter = (unsigned long long *)&t->d_ctrl->absorb_counter;
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)aggregate_kernel, kAggThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_fn(), agg_threads(), smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const uint64_t items = (uint64_t)pl.n_parts * pl.groups;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(items, (uint64_t)c->sms * per_sm));
-    aggregate_kernel<<<grid, kAggThreads, smem, c->stream>>>(a);
+    TRY(launch_aggregate(a, grid, smem, c->stream));
     LAUNCHED();
     CU(cudaGetLastError());
     return OXG_OK;

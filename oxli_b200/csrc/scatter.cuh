@@ -16,13 +16,16 @@
 //
 // A CTA of 12 warps (two per SM) works in rounds: every warp hashes one tile of 256 window starts
 // (8 per lane), then the CTA
-//   1. ranks:   rank = atomicAdd(arrivals[dest], 1)                          | barrier
-//   2. places:  q = accepted[dest] + rank is the hash's position in the fragment; the line being
-//               completed is filled in shared memory, entries of further complete lines (rare)
-//               go straight out, what lies beyond the last complete line waits;
-//               lists the destinations that have a complete line             | barrier
-//   3. flushes: completed lines, 2^line_shift lanes per line                 | barrier
-//   4. moves the waiting entries in at the front of their line, updates the books | barrier
+//   1. ranks:   q = atomicAdd(arrivals[dest], 1) is the hash's position in the fragment | barrier
+//   2. places:  the line that was being filled is completed in shared memory (whoever takes its
+//               last slot lists the destination), entries of further complete lines (rare) go
+//               straight out, what lies beyond the last complete line waits       | barrier
+//   3. flushes: listed lines, 32 bytes per lane                                   | barrier
+//   4. moves the waiting entries in at the front of their line; whoever took a destination's
+//      last position of the round brings its book up to date       (no barrier: step 1 of the
+//      next round touches other words, and its barrier precedes every reader)
+// There is no per-destination loop anywhere: all bookkeeping is done by the threads that hold
+// the hashes.
 // At the end of a launch the last line of every destination goes out padded with zeros (0 is
 // never a hash here, src/lib.rs:589), so fill counts stay multiples of the line and a later
 // launch can continue the same fragments (frag_append): pass B then runs once per several
@@ -66,7 +69,6 @@ __global__ void __launch_bounds__(kScatThreads, kScatCtasPerSm) scatter_kernel(c
     extern __shared__ __align__(128) uint8_t sm[];
     const uint32_t nd = p.n_dest, ls = p.line_shift, line = 1u << ls;
     uint64_t *stage = reinterpret_cast<uint64_t *>(sm);                       // [nd][line]
-    // book[d] = {entries accepted so far (in the fragment or staged), arrivals of this round}
     uint2 *book = reinterpret_cast<uint2 *>(sm + ((size_t)nd << (ls + 3)));  // [nd]
     uint32_t *flist = reinterpret_cast<uint32_t *>(book + nd);                // [nd] destinations to flush this round
     uint32_t *s_nflush = flist + nd;                                          // [4]
@@ -78,11 +80,14 @@ __global__ void __launch_bounds__(kScatThreads, kScatCtasPerSm) scatter_kernel(c
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t frag_row = (uint64_t)gridDim.x * p.frag_cap;              // entries between destinations
     uint64_t *const my_frag = p.frag + (uint64_t)blockIdx.x * p.frag_cap;    // + dest * frag_row
-    // a launch may continue fragments an earlier launch began (frag_append): their fill counts are
-    // multiples of the line, because every launch pads its last lines with zeros (pass B skips them)
-    for (uint32_t i = threadIdx.x; i < nd; i += kScatThreads)
-        book[i] = make_uint2(p.frag_append ? p.frag_cnt[(uint64_t)i * gridDim.x + blockIdx.x] : 0u, 0u);
-    for (uint32_t i = threadIdx.x; i < (nd << ls); i += kScatThreads) stage[i] = 0;
+    // book[d] = {x: entries of the fragment accounted for at the start of the round,
+    //            y: arrivals ever (never reset: an arrival's rank IS its position in the fragment)}
+    // A launch may continue fragments an earlier launch began (frag_append): their fill counts are
+    // multiples of the line, because every launch pads its last lines with zeros (pass B skips them).
+    for (uint32_t i = threadIdx.x; i < nd; i += kScatThreads) {
+        const uint32_t at = p.frag_append ? p.frag_cnt[(uint64_t)i * gridDim.x + blockIdx.x] : 0u;
+        book[i] = make_uint2(at, at);
+    }
     if (threadIdx.x == 0) *s_nflush = 0;
     __syncthreads();
 
@@ -114,6 +119,9 @@ __global__ void __launch_bounds__(kScatThreads, kScatCtasPerSm) scatter_kernel(c
     fetch(tile_of(0), raw, tf);
     off = fetch_off(tile_of(0), tf);
 
+    // a line leaves as 2^(ls-2) lanes x 4 entries: two 128-bit shared loads, one 256-bit store
+    const uint32_t lanes_per_line = ls >= 2 ? (line >> 2) : 1u;
+
     for (uint64_t r = 0; r < n_rounds; ++r) {
         const uint64_t t = tile_of(r);
         uint4 raw_next = make_uint4(0, 0, 0, 0);
@@ -143,41 +151,36 @@ __global__ void __launch_bounds__(kScatThreads, kScatCtasPerSm) scatter_kernel(c
         }
         const uint64_t off_next = fetch_off(tile_of(r + 1), tf_next);  // its tile_first entry has arrived by now
 
-        // 1. rank every hash inside its destination's arrivals of this round
-        uint32_t dst[kWPT], rank[kWPT];
+        // 1. every hash takes its position q in its destination's fragment
+        uint32_t dst[kWPT], q[kWPT];
 #pragma unroll
         for (int j = 0; j < kWPT; ++j) {
-            dst[j] = 0; rank[j] = 0;
-            if (h[j] != 0) { ++n_counted; dst[j] = dest_of(h[j]); rank[j] = atomicAdd(&book[dst[j]].y, 1u); }
+            dst[j] = 0; q[j] = 0;
+            if (h[j] != 0) { ++n_counted; dst[j] = dest_of(h[j]); q[j] = atomicAdd(&book[dst[j]].y, 1u); }
         }
         __syncthreads();
 
-        // 2. place: absolute position q in the fragment; the line being completed is filled in
-        //    shared memory, entries of further complete lines (rare) go straight out, what lies
-        //    beyond the last complete line waits for the flush.  List the destinations to flush.
-        uint32_t later = 0, spilled = 0;
+        // 2. place.  With b.x = entries accounted for before this round and total = what the
+        //    fragment holds after it: positions inside the line that was being filled go into the
+        //    staged line (whoever takes its last slot lists the destination for the flush);
+        //    positions in further complete lines (rare) go straight out; positions beyond the last
+        //    complete line wait for the flush; positions beyond the fragment spill.
+        uint32_t later = 0, spilled = 0, last = 0;
+        uint2 bk[kWPT];  // all books first: the loads are independent, the stores below are not
+#pragma unroll
+        for (int j = 0; j < kWPT; ++j) bk[j] = book[dst[j]];
 #pragma unroll
         for (int j = 0; j < kWPT; ++j) {
             if (h[j] == 0) continue;
-            const uint2 b = book[dst[j]];
-            const uint32_t total = min(b.x + b.y, p.frag_cap), full = total & ~(line - 1);
-            const uint32_t q = b.x + rank[j];
-            if (q >= total) spilled |= 1u << j;                                        // the fragment is full
-            else if (q < (b.x & ~(line - 1)) + line) stage[((size_t)dst[j] << ls) + (q & (line - 1))] = h[j];
-            else if (q < full) my_frag[dst[j] * frag_row + q] = h[j];
-            else { later |= 1u << j; rank[j] = q; }
-        }
-        for (uint32_t d = threadIdx.x; d < ((nd + 31) & ~31u); d += kScatThreads) {
-            bool flush = false;
-            if (d < nd) {
-                const uint2 b = book[d];
-                flush = min(b.x + b.y, p.frag_cap) >= (b.x & ~(line - 1)) + line;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, flush);
-            uint32_t base = 0;
-            if (lane == 0 && m) base = atomicAdd(s_nflush, (uint32_t)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (flush) flist[base + __popc(m & ((1u << lane) - 1))] = d;
+            const uint2 b = bk[j];
+            const uint32_t total = min(b.y, p.frag_cap), line_end = (b.x & ~(line - 1)) + line;
+            if (q[j] >= total) { spilled |= 1u << j; continue; }
+            if (q[j] + 1 == total) last |= 1u << j;
+            if (q[j] < line_end) {
+                stage[((size_t)dst[j] << ls) + (q[j] & (line - 1))] = h[j];
+                if (q[j] + 1 == line_end) flist[atomicAdd(s_nflush, 1u)] = dst[j];
+            } else if (q[j] < (total & ~(line - 1))) my_frag[dst[j] * frag_row + q[j]] = h[j];
+            else later |= 1u << j;
         }
         if (__any_sync(0xffffffffu, spilled != 0)) {
             // skewed input (one k-mer flooding its partition): one reservation per warp tile
@@ -197,30 +200,42 @@ __global__ void __launch_bounds__(kScatThreads, kScatCtasPerSm) scatter_kernel(c
         }
         __syncthreads();
 
-        // 3. flush the completed lines: `line` consecutive lanes write one line
+        // 3. flush the completed lines
         {
             const uint32_t n_flush = *s_nflush;
-            const uint32_t per_warp = 32u >> ls, sub = lane >> ls, li = lane & (line - 1);
-            for (uint32_t e = warp * per_warp + sub; e < n_flush; e += kScatWarps * per_warp) {
-                const uint32_t d = flist[e];
-                my_frag[d * frag_row + (book[d].x & ~(line - 1)) + li] = stage[((size_t)d << ls) + li];
+            if (ls >= 2) {
+                const uint32_t per_warp = 32u / lanes_per_line, sub = lane / lanes_per_line, li = (lane % lanes_per_line) * 4;
+                for (uint32_t e = warp * per_warp + sub; e < n_flush; e += kScatWarps * per_warp) {
+                    const uint32_t d = flist[e];
+                    const uint64_t *src = stage + ((size_t)d << ls) + li;
+                    const ulonglong2 v0 = *reinterpret_cast<const ulonglong2 *>(src), v1 = *reinterpret_cast<const ulonglong2 *>(src + 2);
+                    uint64_t *dstp = my_frag + d * frag_row + (book[d].x & ~(line - 1)) + li;
+                    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(dstp), "l"(v0.x), "l"(v0.y), "l"(v1.x), "l"(v1.y) : "memory");
+                }
+            } else {
+                const uint32_t per_warp = 32u >> ls, sub = lane >> ls, li = lane & (line - 1);
+                for (uint32_t e = warp * per_warp + sub; e < n_flush; e += kScatWarps * per_warp) {
+                    const uint32_t d = flist[e];
+                    my_frag[d * frag_row + (book[d].x & ~(line - 1)) + li] = stage[((size_t)d << ls) + li];
+                }
             }
         }
         __syncthreads();
 
-        // 4. what lies beyond the flushed lines moves in at the front of its line; the books
+        // 4. what lies beyond the flushed lines moves in at the front of its line; whoever took a
+        //    destination's last position of the round brings its book up to date
 #pragma unroll
-        for (int j = 0; j < kWPT; ++j)
-            if ((later >> j) & 1u) stage[((size_t)dst[j] << ls) + (rank[j] & (line - 1))] = h[j];
-        for (uint32_t d = threadIdx.x; d < nd; d += kScatThreads) {
-            const uint2 b = book[d];
-            book[d] = make_uint2(min(b.x + b.y, p.frag_cap), 0u);
+        for (int j = 0; j < kWPT; ++j) {
+            if ((later >> j) & 1u) stage[((size_t)dst[j] << ls) + (q[j] & (line - 1))] = h[j];
+            if ((last >> j) & 1u) book[dst[j]].x = q[j] + 1;
         }
         if (threadIdx.x == 0) *s_nflush = 0;
-        __syncthreads();
+        // (no barrier here: the next round's step 1 touches only the arrival counters, and its
+        // barrier comes before anything reads what step 4 wrote)
         raw = raw_next; tf = tf_next; off = off_next;
     }
 
+    __syncthreads();
     // what is still staged: the last line of every destination goes out whole, its unused slots
     // holding 0 (never a hash: pass A drops it, src/lib.rs:589) so that fill counts stay multiples
     // of the line and a later launch can continue the fragment
