@@ -420,12 +420,25 @@ oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
 
 // ---- partitioned pipeline: pass A (hash + scatter) and pass B (aggregate + merge) -----------
 
+// Which pipeline a counting launch of `span` windows takes.  Measured on one B200
+// (profiles/r2_pipeline_choice.txt): the partitioned pipeline matches the fused kernel on a hot
+// table (C2: 31.4 vs 31.0 ms per step), is 30x faster on low-complexity input (every window the
+// same k-mer: the fused kernel's REDs all hit one address) and is slower when nearly every key
+// is new (C3-shaped: 11.3 vs 14.6 G k-mers/s -- nothing to pre-reduce, and the detour through
+// fragments is pure cost).  So: small launches stay fused; a group of launches is partitioned
+// when it brings at least four occurrences per key the table is known (or hinted) to hold, or
+// when nothing is known yet -- the first group of a new table pays at most the detour and tells.
 bool use_partitioned(const oxg_table *t, uint64_t span) {
     if (!specialised_entry(t->k, kModePart)) return false;
     const int choice = g_pipeline.load();
     if (choice == 1) return false;
     if (choice == 2) return true;
-    return span >= kPartMinWindows;
+    if (span < kPartMinWindows) return false;
+    if (t->pend.active) return true;  // a group in flight is completed the way it began
+    const uint64_t keys = std::max(t->size + t->last_new, t->hint_keys);
+    if (keys == 0) return true;
+    const uint64_t group = std::min<uint64_t>(std::max<uint64_t>(t->part_budget, span), (uint64_t)g_accumulate.load() * kLaunchWindows);
+    return group >= 4 * keys;
 }
 
 // Partition count: about 4096 distinct keys per partition, so that the shared-memory table of

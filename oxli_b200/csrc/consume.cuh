@@ -587,6 +587,19 @@ __global__ void __launch_bounds__(kThreads, K > 32 ? 2 : OXG_MIN_CTAS) consume_k
                 for (int j = 0; j < kWPT; ++j)
                     if (gp0 + j >= p.w_lo && gp0 + j < p.w_hi) p.hashes_out[gp0 + j - p.w_lo] = h[j];
             } else if (kCounts) {
+                // Warp-aggregated pre-reduction for the one pattern that ruins a RED-per-window
+                // scheme: a lane whose eight windows are one and the same k-mer (homopolymer and
+                // two-base-repeat reads: one canonical k-mer for every window).  Such lanes pool
+                // their occurrences with the other lanes of the warp that hold the same hash, and
+                // one of them makes a single update.
+                if (h[0] != 0 && h[0] == h[1] && h[0] == h[2] && h[0] == h[3] && h[0] == h[4] && h[0] == h[5] &&
+                    h[0] == h[6] && h[0] == h[7]) {
+                    const unsigned peers = __match_any_sync(__activemask(), h[0]);
+                    if (lane == __ffs(peers) - 1) created += table_add(p.table, h[0], (uint64_t)kWPT * __popc(peers), full);
+                    n_counted += kWPT;
+#pragma unroll
+                    for (int j = 0; j < kWPT; ++j) h[j] = 0;
+                }
                 while (queue.n > kQueueCap - kWPT * 32) slow_round(p.table, queue, full, created);
                 count_fast8(p.table, h, queue, n_counted);
                 slow_round(p.table, queue, full, created);
