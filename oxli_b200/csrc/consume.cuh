@@ -587,18 +587,27 @@ __global__ void __launch_bounds__(kThreads, K > 32 ? 2 : OXG_MIN_CTAS) consume_k
                 for (int j = 0; j < kWPT; ++j)
                     if (gp0 + j >= p.w_lo && gp0 + j < p.w_hi) p.hashes_out[gp0 + j - p.w_lo] = h[j];
             } else if (kCounts) {
-                // Warp-aggregated pre-reduction for the one pattern that ruins a RED-per-window
-                // scheme: a lane whose eight windows are one and the same k-mer (homopolymer and
-                // two-base-repeat reads: one canonical k-mer for every window).  Such lanes pool
-                // their occurrences with the other lanes of the warp that hold the same hash, and
-                // one of them makes a single update.
-                if (h[0] != 0 && h[0] == h[1] && h[0] == h[2] && h[0] == h[3] && h[0] == h[4] && h[0] == h[5] &&
-                    h[0] == h[6] && h[0] == h[7]) {
-                    const unsigned peers = __match_any_sync(__activemask(), h[0]);
-                    if (lane == __ffs(peers) - 1) created += table_add(p.table, h[0], (uint64_t)kWPT * __popc(peers), full);
-                    n_counted += kWPT;
+                // Warp-aggregated pre-reduction of duplicate hashes, for the pattern that ruins a
+                // RED-per-window scheme: low-complexity sequence (homopolymers, short tandem
+                // repeats), where a lane's eight windows are a handful of k-mers over and over
+                // and every lane of the tile holds the same ones.  A lane that finds one of its
+                // hashes at least twice among its eight pools the occurrences with the lanes of
+                // the warp that hold the same hash; one of them makes a single update.  Ordinary
+                // sequence leaves after eight comparisons.
+                for (int round = 0; round < 4; ++round) {
+                    uint64_t hv = 0;
 #pragma unroll
-                    for (int j = 0; j < kWPT; ++j) h[j] = 0;
+                    for (int j = kWPT - 1; j >= 0; --j) hv = h[j] != 0 ? h[j] : hv;  // first hash still to count
+                    uint32_t same = 0;
+#pragma unroll
+                    for (int j = 0; j < kWPT; ++j) same |= (uint32_t)(hv != 0 && h[j] == hv) << j;
+                    if (__popc(same) < 2) break;
+                    const unsigned peers = __match_any_sync(__activemask(), hv);
+                    const uint32_t occurrences = __reduce_add_sync(peers, (uint32_t)__popc(same));
+                    if (lane == __ffs(peers) - 1) created += table_add(p.table, hv, occurrences, full);
+                    n_counted += __popc(same);
+#pragma unroll
+                    for (int j = 0; j < kWPT; ++j) h[j] = ((same >> j) & 1u) ? 0 : h[j];
                 }
                 while (queue.n > kQueueCap - kWPT * 32) slow_round(p.table, queue, full, created);
                 count_fast8(p.table, h, queue, n_counted);
