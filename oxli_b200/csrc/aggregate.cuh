@@ -56,6 +56,7 @@ struct AggParams {
     uint32_t frag_cap;
     uint32_t part_bits;   // log2(n_parts)
     uint32_t groups;      // work items per partition: item (part, g) takes the fragments f with f % groups == g
+    uint32_t use_cache;   // 0: nothing to pre-reduce (nearly every key new): update the table directly
     uint64_t spill_cap;
     int owner_shift, self_rank, n_ranks;  // owner(h) = h >> owner_shift, for the spill lists
     unsigned long long *work_counter;     // zeroed before the launch
@@ -127,12 +128,15 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_kernel(const AggPara
         // (a straight-line "home buckets of all U first, probe loop for the rest" variant was
         // measured slower, 14.6 vs 9.4 ms per C2 step: the loop below already exits on its first
         // iteration nine times out of ten, and the variant loads every bucket twice on a miss)
-        uint32_t direct = 0;
+        uint32_t direct = live;
+        if (p.use_cache) {
+            direct = 0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (!((live >> u) & 1u)) continue;
-            const uint32_t idx = (uint32_t)(((h[u] * kPhi) << p.part_bits) >> (64 - kLocalBits));
-            if (h[u] == kEmpty || !local_count(lk, ld, h[u], idx)) direct |= 1u << u;
+            for (int u = 0; u < U; ++u) {
+                if (!((live >> u) & 1u)) continue;
+                const uint32_t idx = (uint32_t)(((h[u] * kPhi) << p.part_bits) >> (64 - kLocalBits));
+                if (h[u] == kEmpty || !local_count(lk, ld, h[u], idx)) direct |= 1u << u;
+            }
         }
         if (direct) {  // two at a time: four sets of bucket registers do not fit the register budget
             const uint64_t one[2] = {1, 1};
@@ -165,10 +169,12 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_kernel(const AggPara
         __syncthreads();  // previous item fully merged; s_item free
         if (threadIdx.x == 0) { s_item = atomicAdd(p.work_counter, 1ULL); s_next = 0; }
         // empty the cache
-        for (uint32_t i = threadIdx.x; i < kLocalSlots / 2; i += kAggThreads)
-            reinterpret_cast<ulonglong2 *>(lk)[i] = make_ulonglong2(kEmpty, kEmpty);
-        for (uint32_t i = threadIdx.x; i < kLocalSlots / 4; i += kAggThreads)
-            reinterpret_cast<uint4 *>(ld)[i] = make_uint4(0, 0, 0, 0);
+        if (p.use_cache) {
+            for (uint32_t i = threadIdx.x; i < kLocalSlots / 2; i += kAggThreads)
+                reinterpret_cast<ulonglong2 *>(lk)[i] = make_ulonglong2(kEmpty, kEmpty);
+            for (uint32_t i = threadIdx.x; i < kLocalSlots / 4; i += kAggThreads)
+                reinterpret_cast<uint4 *>(ld)[i] = make_uint4(0, 0, 0, 0);
+        }
         __syncthreads();
         const uint64_t item = s_item;
         if (item >= n_items) break;
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_kernel(const AggPara
 
         // merge: distinct keys of this item, in slot order of the table (the cache index is the
         // next-lower bits of the same product h * phi)
-        {
+        if (p.use_cache) {
             constexpr int M = 2;
             for (uint32_t base = 0; base < kLocalSlots; base += kAggThreads * M) {
                 uint64_t key[M], inc[M];

@@ -546,8 +546,15 @@ oxg_status launch_aggregate(const AggParams &a, int grid, size_t smem, cudaStrea
     return OXG_OK;
 }
 
+// The shared-memory table of pass B pays when keys repeat inside what it is given: at least two
+// occurrences per key the table is known to hold (an empty table tells nothing: cache on).
+uint32_t use_cache_for(const oxg_table *t, uint64_t windows) {
+    const uint64_t keys = std::max(t->size, t->hint_keys);
+    return keys == 0 || windows >= 2 * keys ? 1u : 0u;
+}
+
 // pass B over n_src sources (one, this device's own pass A output, without sharding)
-oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src, int n_src) {
+oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src, int n_src, uint64_t windows) {
     DeviceCtx *c = t->ctx;
     const size_t smem = aggregate_smem_bytes();
     if (!c->agg_attr_done) {
@@ -562,6 +569,7 @@ oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src,
     a.frag_cap = pl.frag_cap; a.part_bits = pl.part_bits; a.groups = pl.groups; a.spill_cap = pl.spill_cap;
     a.owner_shift = pl.owner_shift; a.self_rank = pl.self_rank; a.n_ranks = pl.n_ranks;
     a.work_counter = (unsigned long long *)&t->d_ctrl->absorb_counter;
+    a.use_cache = use_cache_for(t, windows);
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_fn(), agg_threads(), smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const uint64_t items = (uint64_t)pl.n_parts * pl.groups;
@@ -579,7 +587,7 @@ oxg_status flush_pending(oxg_table *t, uint64_t *counted) {
     t->pend.active = false;
     CU(cudaEventRecord(c->ev_mid, c->stream));
     const AggSource own{c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n};
-    TRY(launch_part_b(t, t->pend.pl, &own, 1));
+    TRY(launch_part_b(t, t->pend.pl, &own, 1, t->pend.windows));
     CU(cudaEventRecord(c->ev_t1, c->stream));
     const uint64_t size_before = t->size;
     TRY(pull_ctrl(t));

@@ -111,6 +111,23 @@ def test_growth_from_tiny_table_and_singletons(capi, part):
     assert_same_table(t, ora)
 
 
+def test_direct_mode_when_nothing_repeats(capi, part):
+    # a hint far above the launch size tells pass B that nearly every key is new: it then updates
+    # the table directly instead of going through its shared-memory table
+    bases = synth_reads(30_000, 150, 80_000_000, seed=21, sub_ppm=5_000, n_ppm=500)
+    offs = uniform_offsets(30_000, 150)
+    for k in (21, 31):
+        ora = OracleTable(k)
+        want, _, _ = ora.consume_batch(bases, offs, True, nthreads=4)
+        t = capi.Table(k, capacity_hint=50_000_000)
+        st, total, _, _ = t.consume_batch(bases, offs, True)
+        assert (st, total) == (0, want)
+        st, total, _, _ = t.consume_batch(bases[: 150 * 10_000], offs[:10_001], True)  # a second batch on top
+        want2, _, _ = ora.consume_batch(bases[: 150 * 10_000], offs[:10_001], True, nthreads=4)
+        assert (st, total) == (0, want2)
+        assert_same_table(t, ora)
+
+
 def test_error_mode_goes_through_the_same_pipeline(capi, part):
     rng = np.random.default_rng(9)
     clean, offs = ragged_batch(rng, 2000, 220, p_bad=0.0, p_empty=0.05)
