@@ -20,6 +20,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/oxli_b200.h"
 #include "aggregate.cuh"
@@ -66,6 +67,14 @@ oxg_status fail(oxg_status st, const char *fmt, ...) {
         if (s__ != OXG_OK) return s__;     \
     } while (0)
 #define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// NVTX ranges around the stages of an ingest call (copy / scatter / aggregate / fused consume /
+// replay / shard round), so that a timeline of the end-to-end step can be read; free without a
+// profiler attached
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // host->device streaming granule: OXLI_B200_CHUNK_MB in 1..1024, anything else means the default
 static const uint64_t kChunkBytes = [] {
@@ -340,6 +349,7 @@ oxg_status reserve_keys(oxg_table *t, uint64_t extra) { return grow_to_fit(t, t-
 // at most as many new keys as the table already holds -- and replay; a replay that runs into
 // the limit again defers into the second list and the loop goes round once more.
 oxg_status drain_deferred(oxg_table *t, uint64_t ov, bool may_allocate = true) {
+    NvtxRange range("oxg:replay deferred");
     DeviceCtx *c = t->ctx;
     if (ov > c->overflow_cap) return fail(OXG_ERR_CUDA, "internal: overflow list overrun");
     uint64_t prev = ~0ULL;
@@ -583,6 +593,7 @@ oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src,
 // pass B for the pass A launches accumulated so far, then the bookkeeping of a counting launch
 oxg_status flush_pending(oxg_table *t, uint64_t *counted) {
     if (!t->pend.active) return OXG_OK;
+    NvtxRange range("oxg:aggregate (pass B)");
     DeviceCtx *c = t->ctx;
     t->pend.active = false;
     CU(cudaEventRecord(c->ev_mid, c->stream));
@@ -656,6 +667,7 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
         CU(cudaGetLastError());
         const bool part = mode == kModeCount && use_partitioned(t, hi - lo);
         if (part) {
+            NvtxRange range("oxg:scatter (pass A)");
             // pass A now; pass B once the group of launches is complete (flush_pending)
             const uint64_t span = hi - lo;
             if (t->pend.active && t->pend.windows + span > t->pend.planned) TRY(flush_pending(t, counted));
@@ -673,6 +685,7 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
             lo = hi;
             continue;
         }
+        NvtxRange range(mode == kModeCount ? "oxg:consume (fused)" : mode == kModeHash ? "oxg:hash windows" : "oxg:first-bad scan");
         CU(cudaEventRecord(c->ev_t0, c->stream));
         if (mode == kModeCount) TRY(launch_consume<kModeCount>(t, p));
         else if (mode == kModeHash) TRY(launch_consume<kModeHash>(t, p));
@@ -978,6 +991,7 @@ static oxg_status stream_span(oxg_table *t, int mode, const uint8_t *bases, cons
     };
     // the previous use of buffer b (chunk ci - kStageBufs) is over: its kernels were waited for
     auto issue_copy = [&](uint64_t ci) -> oxg_status {
+        NvtxRange range("oxg:stage + H2D copy");
         const int b = (int)(ci % kStageBufs);
         // every chunk also validates its share of the offsets (all pairs are seen once per call),
         // so the O(n_reads) pass runs on the producer thread next to the copies instead of in

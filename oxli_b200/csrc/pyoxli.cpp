@@ -13,8 +13,10 @@
 //   KmerCountTable(ksize, store_kmers=False, *, device=0, capacity_hint=0)
 //   consume_many(seqs, skip_bad_kmers=True)      one GPU batch for many reads
 //   consume_buffer(bases, offsets, skip_bad_kmers=True)   CSR batch, zero-copy from buffers
-//   KmerCountTable(..., deferred=True)           consume(seq) parks reads in a pinned batch and
-//                                                 returns at host speed; see Table::sync
+//   KmerCountTable(..., deferred=True)           the default: consume(seq) parks reads in a pinned
+//                                                 batch and returns at host speed (see Table::sync);
+//                                                 deferred=False or OXLI_B200_DEFERRED=0: one
+//                                                 synchronous GPU call per consume(seq)
 //   consume_file(path, skip_bad_kmers=True)      FASTA/FASTQ (plain or gzip) parsed into pinned
 //                                                 batches -- the loop the reference leaves to
 //                                                 screed (README.md:89-98)
@@ -300,15 +302,30 @@ struct Table {
             }
             if (!good.empty()) ck(oxg_count_hashes(h, good.data(), good.size(), nullptr));
             n = good.size();
-        } else if (deferred && skip_bad) {
-            // host scan: windows without a non-ACGT byte (what the device will count; the
-            // reference's hash==0 skip, probability 2^-64 per k-mer, is not visible here)
+        } else if (deferred) {
+            // The per-record loop of the reference's README (`for record in ...: t.consume(seq)`)
+            // must not pay a kernel launch per 150-bp read: the read is parked in a pinned batch
+            // that goes to the GPU when it fills up or when any other method needs the table.
+            // What the call returns comes from a host scan: windows without a non-ACGT byte --
+            // exactly what the device counts, except for the reference's hash==0 skip
+            // (src/lib.rs:589; probability 2^-64 per k-mer), which the scan cannot see.
             if (!pending) pending = std::make_unique<PinnedBatch>(1 << 20);  // doubles as reads arrive, flushed at kPendingBytes
-            int64_t last_bad = -1;
+            int64_t last_bad = -1, first_bad = -1;
             for (size_t i = 0; i < seq.size(); ++i) {
                 const char c = seq[i] & ~0x20;
-                if (!is_acgt(c)) last_bad = (int64_t)i;
+                if (!is_acgt(c)) { last_bad = (int64_t)i; if (first_bad < 0) first_bad = (int64_t)i; }
                 if (i + 1 >= ksize && last_bad < (int64_t)(i + 1 - ksize)) ++n;
+            }
+            if (!skip_bad && first_bad >= 0 && seq.size() >= ksize) {
+                // error mode (src/lib.rs:593-596): the windows before the first bad one are counted
+                // and stay counted, then ValueError; `consumed` is not updated on this path
+                const uint64_t w = first_bad + 1 >= (int64_t)ksize ? (uint64_t)(first_bad + 1 - ksize) : 0;
+                if (w > 0) {
+                    pending->append(seq.data(), w + ksize - 1);
+                    pending->end_record();
+                    if (pending->used >= kPendingBytes) sync();
+                }
+                throw py::value_error("bad k-mer encountered at position " + std::to_string(w));
             }
             pending->append(seq.data(), seq.size());
             pending->end_record();
@@ -584,11 +601,11 @@ PYBIND11_MODULE(_oxli, m) {
 
     py::class_<Table>(m, "KmerCountTable")
         .def(py::init([](py::object ksize, bool store_kmers, int device, uint64_t capacity_hint, py::object deferred) {
-                 // deferred=None: OXLI_B200_DEFERRED=1 switches existing per-record scripts over without edits
-                 bool defer = false;
+                 // deferred=None (default): parked consume, unless OXLI_B200_DEFERRED=0 asks for one launch per call
+                 bool defer = true;
                  if (deferred.is_none()) {
                      const char *e = getenv("OXLI_B200_DEFERRED");
-                     defer = e && *e && strcmp(e, "0") != 0;
+                     if (e && *e) defer = strcmp(e, "0") != 0;
                  } else defer = deferred.cast<bool>();
                  return std::make_unique<Table>(ksize_from_py(ksize), store_kmers, device, capacity_hint, defer);
              }),

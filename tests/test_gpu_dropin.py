@@ -325,7 +325,7 @@ def test_deferred_consume_matches_immediate(oxli, example_seq):
     reads[7] = "ACGTN" * 30
     reads[8] = "acgtacgtacgtacgtacgtacgtacgtacgtacgtacgt"
     reads[9] = "ACG"
-    a, d = oxli.KmerCountTable(21), oxli.KmerCountTable(21, deferred=True)
+    a, d = oxli.KmerCountTable(21, deferred=False), oxli.KmerCountTable(21, deferred=True)
     for r in reads:
         assert d.consume(r) == a.consume(r)
     assert d.get(reads[0][:21]) == a.get(reads[0][:21])  # any other call flushes the parked reads
@@ -333,18 +333,47 @@ def test_deferred_consume_matches_immediate(oxli, example_seq):
         assert d.consume(r) == a.consume(r)
     assert len(d) == len(a) and sorted(d) == sorted(a) and d.consumed == a.consumed
     assert d.jaccard(a) == 1.0 and d.histo() == a.histo()
-    with pytest.raises(ValueError, match="bad k-mer encountered at position 0"):
-        d.consume("ACGTN" * 30, skip_bad_kmers=False)  # error mode is never deferred
+    # error mode is parked too: the clean prefix is counted and stays counted, then ValueError with
+    # the reference's message; `consumed` does not move (src/lib.rs:593-596)
+    for bad, pos in (("ACGTN" * 30, 0), (reads[3][:100] + "N" + reads[3][100:], 80), ("N" + reads[4], 0),
+                     (reads[5] + "n", 150 - 21 + 1), (reads[6][:20] + "X", 0)):
+        for t in (a, d):
+            before = t.consumed
+            if len(bad) >= 21:
+                with pytest.raises(ValueError, match=f"bad k-mer encountered at position {pos}$"):
+                    t.consume(bad, skip_bad_kmers=False)
+                assert t.consumed == before
+            else:
+                assert t.consume(bad, skip_bad_kmers=False) == 0 and t.consumed == before + len(bad)
+    assert sorted(d) == sorted(a) and d.consumed == a.consumed
     d.consume(reads[0]); d.flush()
     assert d.get(reads[0][:21]) == a.get(reads[0][:21]) + 1
 
 
-def test_deferred_default_comes_from_the_environment(oxli, monkeypatch):
+def test_deferred_is_the_default_and_the_environment_can_switch_it_off(oxli, monkeypatch):
     monkeypatch.delenv("OXLI_B200_DEFERRED", raising=False)
-    assert oxli.KmerCountTable(21).deferred is False
-    monkeypatch.setenv("OXLI_B200_DEFERRED", "1")
     t = oxli.KmerCountTable(21)
     assert t.deferred is True and oxli.KmerCountTable(21, deferred=False).deferred is False
     assert t.consume("ACGTACGTACGTACGTACGTACGTA") == 5 and 0 < len(t) <= 5
     monkeypatch.setenv("OXLI_B200_DEFERRED", "0")
-    assert oxli.KmerCountTable(21).deferred is False
+    assert oxli.KmerCountTable(21).deferred is False and oxli.KmerCountTable(21, deferred=True).deferred is True
+    monkeypatch.setenv("OXLI_B200_DEFERRED", "1")
+    assert oxli.KmerCountTable(21).deferred is True
+
+
+def test_per_record_loop_runs_at_host_speed(oxli, example_seq):
+    # the reference's usage (README.md:96-98): one consume() per record.  10^5 calls here; the
+    # rate is asserted loosely (CI boxes differ), the number is printed for the record
+    import time
+
+    reads = [example_seq[i:i + 150] for i in range(0, 150 * 2000, 150)] * 50
+    t = oxli.KmerCountTable(31)
+    t0 = time.perf_counter()
+    n = 0
+    for r in reads:
+        n += t.consume(r)
+    total = len(t)  # flushes
+    dt = time.perf_counter() - t0
+    print(f"per-record consume: {len(reads) / dt / 1e6:.2f} M calls/s, {n / dt / 1e6:.1f} M k-mers/s")
+    assert n == 120 * len(reads) and total > 0
+    assert n / dt > 20e6, "the per-record loop fell back to one GPU launch per call"
