@@ -273,6 +273,10 @@ struct oxg_table {
         uint64_t windows = 0, planned = 0;
     } pend;
     uint64_t part_budget = 0;  // windows the running consume call still has to go (0 = unknown)
+    // HyperLogLog sketch of the keys that came in through the partitioned pipeline (aggregate.cuh)
+    uint32_t *d_sketch = nullptr;
+    uint32_t *h_sketch = nullptr;  // pinned
+    uint64_t sketch_covers = 0;    // keys of the table the sketch has seen
     uint64_t last_new = 0;   // keys created by the previous consume launch (growth look-ahead)
     float last_ms = 0.f;
     uint64_t last_launches = 0;
@@ -590,6 +594,44 @@ oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src,
     return OXG_OK;
 }
 
+// HyperLogLog estimate from 2^kSketchBits registers (Flajolet et al.; linear counting below 2.5 m)
+double sketch_estimate(const uint32_t *regs) {
+    const double m = (double)kSketchRegs;
+    double sum = 0.0;
+    uint32_t zeros = 0;
+    for (uint32_t i = 0; i < kSketchRegs; ++i) { sum += std::ldexp(1.0, -(int)regs[i]); zeros += regs[i] == 0; }
+    const double alpha = 0.7213 / (1.0 + 1.079 / m);
+    double e = alpha * m * m / sum;
+    if (e <= 2.5 * m && zeros) e = m * std::log(m / (double)zeros);
+    return e;
+}
+
+// Before pass B: fold the group's hashes into the table's sketch and make room for what the
+// table will hold afterwards -- unless the caller's hint still covers it.  `src` as for pass B.
+oxg_status presize_for_group(oxg_table *t, const PartPlan &pl, const AggSource *src, int n_src, cudaStream_t stream) {
+    DeviceCtx *c = t->ctx;
+    if (!t->d_sketch) {
+        CU(cudaMalloc(&t->d_sketch, kSketchRegs * 4));
+        CU(cudaMallocHost(&t->h_sketch, kSketchRegs * 4));
+        CU(cudaMemsetAsync(t->d_sketch, 0, kSketchRegs * 4, stream));
+    }
+    AggParams a{};
+    for (int s = 0; s < n_src; ++s) a.src[s] = src[s];
+    a.n_src = n_src;
+    a.n_parts = pl.n_parts; a.dest0 = (uint32_t)pl.self_rank * pl.n_parts; a.n_ctas = pl.grid_a;
+    a.frag_cap = pl.frag_cap; a.part_bits = pl.part_bits; a.spill_cap = pl.spill_cap;
+    a.owner_shift = pl.owner_shift; a.self_rank = pl.self_rank; a.n_ranks = pl.n_ranks;
+    sketch_kernel<<<c->sms * 2, 512, 0, stream>>>(a, t->d_sketch);
+    LAUNCHED();
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(t->h_sketch, t->d_sketch, kSketchRegs * 4, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    const uint64_t unseen = t->size > t->sketch_covers ? t->size - t->sketch_covers : 0;  // keys that came in another way
+    const uint64_t expect = (uint64_t)(sketch_estimate(t->h_sketch) * 1.04) + unseen + 1024;  // three standard errors
+    if (expect * 10 > t->cap * 7) TRY(grow_to_fit(t, expect));
+    return OXG_OK;
+}
+
 // pass B for the pass A launches accumulated so far, then the bookkeeping of a counting launch
 oxg_status flush_pending(oxg_table *t, uint64_t *counted) {
     if (!t->pend.active) return OXG_OK;
@@ -598,6 +640,8 @@ oxg_status flush_pending(oxg_table *t, uint64_t *counted) {
     t->pend.active = false;
     CU(cudaEventRecord(c->ev_mid, c->stream));
     const AggSource own{c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n};
+    const bool hint_holds = t->hinted && t->size + t->pend.windows / 64 <= t->hint_keys;
+    if (!hint_holds) TRY(presize_for_group(t, t->pend.pl, &own, 1, c->stream));
     TRY(launch_part_b(t, t->pend.pl, &own, 1, t->pend.windows));
     CU(cudaEventRecord(c->ev_t1, c->stream));
     const uint64_t size_before = t->size;
@@ -613,6 +657,21 @@ oxg_status flush_pending(oxg_table *t, uint64_t *counted) {
     const uint64_t made = t->size - size_before;
     t->last_new = ov ? made + ov : (t->hinted && t->size <= t->hint_keys) ? 0 : made;
     if (ov) TRY(drain_deferred(t, ov));
+    if (!hint_holds) {
+        t->sketch_covers = t->size;
+        // Where keys keep coming (a quarter of the windows or more brought a new key), the rest of
+        // the call will bring them at no more than this rate: make the room now, in one step,
+        // rather than by doubling under load.  0.6: the rate of a read set falls as coverage builds
+        // up (C3-shaped input: 0.39 new keys per window in the first group, 0.22 over the whole set).
+        if (made * 4 >= t->pend.windows && t->part_budget) {
+            const uint64_t more = (uint64_t)((double)made / (double)t->pend.windows * 0.6 * (double)t->part_budget);
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            const uint64_t want = t->size + more;
+            const uint64_t cap_want = std::max(capacity_for_keys(want), pow2_at_least(want * 2));
+            if (cap_want > t->cap && cap_want * 16 < free_b / 2) TRY(grow_to_fit(t, want));
+        }
+    }
     return OXG_OK;
 }
 
@@ -810,6 +869,8 @@ oxg_status oxg_table_destroy(oxg_table *t) {
     if (t->pooled) cudaFreeAsync(t->slots, t->ctx->stream); else cudaFree(t->slots);
     cudaFree(t->d_ctrl);
     cudaFreeHost(t->h_ctrl);
+    if (t->d_sketch) cudaFree(t->d_sketch);
+    if (t->h_sketch) cudaFreeHost(t->h_sketch);
     delete t;
     return OXG_OK;
 }
@@ -826,7 +887,10 @@ oxg_status oxg_table_clear(oxg_table *t) {
     LAUNCHED();
     CU(cudaGetLastError());
     CU(cudaMemsetAsync(t->d_ctrl, 0, sizeof(Ctrl), c->stream));
+    if (t->d_sketch) CU(cudaMemsetAsync(t->d_sketch, 0, kSketchRegs * 4, c->stream));
+    t->sketch_covers = 0;
     t->size = 0;
+    t->last_new = 0;
     return OXG_OK;
 }
 

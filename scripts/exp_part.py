@@ -22,6 +22,7 @@ ap.add_argument("--hint", type=int, default=-1)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--configs", default="fused,part,part:512,part:1024,part:2048,part:4096")
 ap.add_argument("--digest", action="store_true")
+ap.add_argument("--fresh", action="store_true", help="a new table every step (growth from nothing is part of the step)")
 a = ap.parse_args()
 
 n, L, k = a.reads, a.read_len, a.ksize
@@ -39,7 +40,11 @@ for cfg in a.configs.split(","):
     t = capi.Table(k, capacity_hint=hint)
     best, split = 1e30, (0, 0)
     for s in range(a.steps + 1):
-        t.clear()
+        if a.fresh:
+            t.close()
+            t = capi.Table(k, capacity_hint=hint)
+        else:
+            t.clear()
         t.timer_start()
         st, total, _, _ = t.consume_batch_device(d_bases, d_offs, n, n * L, True)
         ms = t.timer_stop()
