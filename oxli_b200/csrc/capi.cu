@@ -277,6 +277,7 @@ struct oxg_table {
     uint32_t *d_sketch = nullptr;
     uint32_t *h_sketch = nullptr;  // pinned
     uint64_t sketch_covers = 0;    // keys of the table the sketch has seen
+    uint64_t last_made = 0;        // keys the previous group of launches created
     uint64_t last_new = 0;   // keys created by the previous consume launch (growth look-ahead)
     float last_ms = 0.f;
     uint64_t last_launches = 0;
@@ -640,8 +641,13 @@ oxg_status flush_pending(oxg_table *t, uint64_t *counted) {
     t->pend.active = false;
     CU(cudaEventRecord(c->ev_mid, c->stream));
     const AggSource own{c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n};
-    const bool hint_holds = t->hinted && t->size + t->pend.windows / 64 <= t->hint_keys;
-    if (!hint_holds) TRY(presize_for_group(t, t->pend.pl, &own, 1, c->stream));
+    // The sketch costs a pass over the group's hashes (0.8 ms per 209 M): taken when the table's
+    // size is anybody's guess -- no hint (or the hint is used up), and either nothing is known yet
+    // or the room left would not take twice what the previous group created.
+    const bool hint_holds = t->hinted && t->size <= t->hint_keys;
+    const bool roomy = t->size != 0 && (t->size + 2 * t->last_made) * 10 <= t->cap * 7;
+    const bool sketched = !hint_holds && !roomy;
+    if (sketched) TRY(presize_for_group(t, t->pend.pl, &own, 1, c->stream));
     TRY(launch_part_b(t, t->pend.pl, &own, 1, t->pend.windows));
     CU(cudaEventRecord(c->ev_t1, c->stream));
     const uint64_t size_before = t->size;
@@ -657,8 +663,9 @@ oxg_status flush_pending(oxg_table *t, uint64_t *counted) {
     const uint64_t made = t->size - size_before;
     t->last_new = ov ? made + ov : (t->hinted && t->size <= t->hint_keys) ? 0 : made;
     if (ov) TRY(drain_deferred(t, ov));
+    t->last_made = made;
+    if (sketched) t->sketch_covers = t->size;
     if (!hint_holds) {
-        t->sketch_covers = t->size;
         // Where keys keep coming (a quarter of the windows or more brought a new key), the rest of
         // the call will bring them at no more than this rate: make the room now, in one step,
         // rather than by doubling under load.  0.6: the rate of a read set falls as coverage builds
@@ -889,6 +896,7 @@ oxg_status oxg_table_clear(oxg_table *t) {
     CU(cudaMemsetAsync(t->d_ctrl, 0, sizeof(Ctrl), c->stream));
     if (t->d_sketch) CU(cudaMemsetAsync(t->d_sketch, 0, kSketchRegs * 4, c->stream));
     t->sketch_covers = 0;
+    t->last_made = 0;
     t->size = 0;
     t->last_new = 0;
     return OXG_OK;
