@@ -560,7 +560,22 @@ def run_sharded(a, rank: int, world: int, local: int):
                       mine_err == want_err and np.array_equal(gk, ok_[mine]) and np.array_equal(gv, ov_[mine]))
             sub.close()
 
-    cpu = None
+    # what ONE GPU does with one rank's share of this workload and an unsharded table (the
+    # denominator of weak-scaling efficiency; `bench.py --gpus 1` measures C2, another workload)
+    single = None
+    if rank == 0:
+        t1 = capi.Table(k, device=local)
+        best = 1e30
+        for _ in range(2):
+            t1.clear()
+            t1.timer_start()
+            st, got1, _, _ = t1.consume_batch_device(d_bases, d_offs, n, total_bases, True)
+            best = min(best, t1.timer_stop())
+        single = {"n_gpus": 1, "value": got1 / (best / 1e3), "unit": UNIT, "ms_per_step": best,
+                  "what": f"rank 0's {n} reads alone on one GPU, unsharded table (second of two passes, capacity kept)"}
+        t1.close()
+    dist.barrier()
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         balg = alg_bytes_per_kmer(L, k, world)
@@ -581,7 +596,8 @@ def run_sharded(a, rank: int, world: int, local: int):
                          "frac": achieved / (peak * world), "traffic": None, "alg_bytes_per_kmer": balg,
                          "peak_source": peak_src + f" x {world} GPUs", "scope": "whole step, all ranks",
                          "kernel": f"scatter_kernel<{k}> + aggregate_kernel"},
-            "e2e": e2e, "parity": parity, "gpu_launches": tot_launches, "wall_ms_per_step": wall_ms_per_step,
+            "e2e": e2e, "parity": parity, "single_gpu_same_workload": single, "gpu_launches": tot_launches,
+            "wall_ms_per_step": wall_ms_per_step,
             "timing": "CUDA events on each shard's stream around its rounds, max over ranks",
             "clocks": clocks.summary(),
         }

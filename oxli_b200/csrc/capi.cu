@@ -28,6 +28,7 @@
 #include "scatter.cuh"
 #include "klist.h"
 #include "shard.cuh"
+#include "sortexport.cuh"
 #include "tableops.cuh"
 
 using namespace oxg;
@@ -139,6 +140,13 @@ struct DeviceCtx {
     uint64_t *d_spill = nullptr;      uint64_t spill_cap = 0;
     unsigned long long *d_spill_n = nullptr;
     bool agg_attr_done = false;
+    // export: compacted pairs, the second pair of arrays of the radix sort, its histogram, pinned bounce buffers
+    uint64_t *d_exp_k[2] = {}, *d_exp_v[2] = {};
+    uint64_t exp_cap[2] = {};
+    uint64_t *d_exp_counts = nullptr; uint64_t exp_counts_cap = 0;
+    uint64_t *d_sort_hist = nullptr;  uint64_t sort_hist_cap = 0;
+    uint8_t *h_bounce[2] = {};
+    cudaEvent_t ev_bounce[2] = {};
 };
 
 std::mutex g_ctx_mu;
@@ -1482,27 +1490,92 @@ oxg_status oxg_table_digest(oxg_table *t, int n_ranks, int rank, uint64_t out[5]
 
 // ---- export --------------------------------------------------------------------
 
-static oxg_status export_device(oxg_table *t, uint64_t **d_keys, uint64_t **d_vals, uint64_t *n_live) {
+constexpr uint64_t kBounceBytes = 32ull << 20;
+
+// ordered compaction of the live slots into the context's export arrays [0] (slot order: stable
+// between calls while the table is not modified, so dump() == list(iter), src/lib.rs:330-381,658)
+static oxg_status export_device(oxg_table *t, uint64_t *n_live) {
     DeviceCtx *c = t->ctx;
     const uint64_t n_chunks = (t->cap + kExportChunk - 1) / kExportChunk;
-    uint64_t *d_counts = nullptr;
-    CU(cudaMalloc(&d_counts, (n_chunks + 1) * 8));
-    export_count_kernel<<<(unsigned)n_chunks, kOpThreads, 0, c->stream>>>(t->slots, t->cap, d_counts);
+    TRY(ensure_dev(&c->d_exp_counts, &c->exp_counts_cap, n_chunks + 1));
+    export_count_kernel<<<(unsigned)n_chunks, kOpThreads, 0, c->stream>>>(t->slots, t->cap, c->d_exp_counts);
     LAUNCHED();
-    export_scan_kernel<<<1, 1024, 0, c->stream>>>(d_counts, n_chunks, d_counts + n_chunks);
+    export_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_exp_counts, n_chunks, c->d_exp_counts + n_chunks);
     LAUNCHED();
     CU(cudaGetLastError());
     uint64_t live = 0;
-    CU(cudaMemcpyAsync(&live, d_counts + n_chunks, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&live, c->d_exp_counts + n_chunks, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    CU(cudaMalloc(d_keys, std::max<uint64_t>(live, 1) * 8));
-    CU(cudaMalloc(d_vals, std::max<uint64_t>(live, 1) * 8));
-    export_write_kernel<<<(unsigned)n_chunks, kOpThreads, 0, c->stream>>>(t->slots, t->cap, d_counts, *d_keys, *d_vals, live);
+    if (c->exp_cap[0] < live + 1) {
+        if (c->d_exp_k[0]) { CU(cudaFree(c->d_exp_k[0])); CU(cudaFree(c->d_exp_v[0])); }
+        c->d_exp_k[0] = c->d_exp_v[0] = nullptr; c->exp_cap[0] = 0;
+        CU(cudaMalloc(&c->d_exp_k[0], (live + 1) * 8));
+        CU(cudaMalloc(&c->d_exp_v[0], (live + 1) * 8));
+        c->exp_cap[0] = live + 1;
+    }
+    export_write_kernel<<<(unsigned)n_chunks, kOpThreads, 0, c->stream>>>(t->slots, t->cap, c->d_exp_counts, c->d_exp_k[0], c->d_exp_v[0], live);
     LAUNCHED();
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaFree(d_counts));
     *n_live = live;
+    return OXG_OK;
+}
+
+// stable LSD radix sort of the n pairs in export arrays [0]; *which = the pair of arrays holding the result
+static oxg_status sort_pairs_device(DeviceCtx *c, uint64_t n, int sort_mode, uint64_t max_count, int *which) {
+    *which = 0;
+    if (n < 2) return OXG_OK;
+    if (c->exp_cap[1] < n) {
+        if (c->d_exp_k[1]) { CU(cudaFree(c->d_exp_k[1])); CU(cudaFree(c->d_exp_v[1])); }
+        c->d_exp_k[1] = c->d_exp_v[1] = nullptr; c->exp_cap[1] = 0;
+        CU(cudaMalloc(&c->d_exp_k[1], n * 8));
+        CU(cudaMalloc(&c->d_exp_v[1], n * 8));
+        c->exp_cap[1] = n;
+    }
+    const uint64_t n_tiles = (n + kSortTile - 1) / kSortTile;
+    TRY(ensure_dev(&c->d_sort_hist, &c->sort_hist_cap, 256 * n_tiles));
+    int cur = 0;
+    auto pass = [&](int shift, int by_count) -> oxg_status {
+        radix_hist_kernel<<<(unsigned)n_tiles, kSortThreads, 0, c->stream>>>(c->d_exp_k[cur], c->d_exp_v[cur], n, shift, by_count, n_tiles, c->d_sort_hist);
+        LAUNCHED();
+        radix_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_sort_hist, 256 * n_tiles);
+        LAUNCHED();
+        radix_scatter_kernel<<<(unsigned)n_tiles, kSortThreads, 0, c->stream>>>(c->d_exp_k[cur], c->d_exp_v[cur], c->d_exp_k[cur ^ 1], c->d_exp_v[cur ^ 1],
+                                                                                n, shift, by_count, n_tiles, c->d_sort_hist);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        cur ^= 1;
+        return OXG_OK;
+    };
+    for (int shift = 0; shift < 64; shift += 8) TRY(pass(shift, 0));           // by hash
+    if (sort_mode == 2)                                                        // then, stably, by count
+        for (int shift = 0; shift < 64 && (max_count >> shift) != 0; shift += 8) TRY(pass(shift, 1));
+    *which = cur;
+    return OXG_OK;
+}
+
+// device array -> caller's host array through two pinned bounce buffers (the caller's memory is
+// usually pageable: a plain cudaMemcpy would stage it the same way, but one chunk at a time)
+static oxg_status download(DeviceCtx *c, uint64_t *dst, const uint64_t *d_src, uint64_t n) {
+    if (!dst || n == 0) return OXG_OK;
+    for (int b = 0; b < 2; ++b)
+        if (!c->h_bounce[b]) {
+            CU(cudaMallocHost(&c->h_bounce[b], kBounceBytes));
+            CU(cudaEventCreateWithFlags(&c->ev_bounce[b], cudaEventDisableTiming));
+        }
+    const uint64_t per = kBounceBytes / 8;
+    const uint64_t n_chunks = (n + per - 1) / per;
+    for (uint64_t i = 0; i <= n_chunks; ++i) {
+        if (i < n_chunks) {
+            const uint64_t lo = i * per, cnt = std::min(per, n - lo);
+            CU(cudaMemcpyAsync(c->h_bounce[i & 1], d_src + lo, cnt * 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaEventRecord(c->ev_bounce[i & 1], c->stream));
+        }
+        if (i > 0) {  // chunk i-1 has landed while chunk i is on its way
+            const uint64_t lo = (i - 1) * per, cnt = std::min(per, n - lo);
+            CU(cudaEventSynchronize(c->ev_bounce[(i - 1) & 1]));
+            memcpy(dst + lo, c->h_bounce[(i - 1) & 1], cnt * 8);
+        }
+    }
     return OXG_OK;
 }
 
@@ -1512,29 +1585,31 @@ oxg_status oxg_export(oxg_table *t, uint64_t *keys, uint64_t *vals, uint64_t cap
     if (sort_mode < 0 || sort_mode > 2) return fail(OXG_ERR_INVALID, "sort_mode must be 0, 1 or 2");
     TRY(pull_ctrl(t));
     const bool side = t->h_ctrl->side_present != 0;
+    const uint64_t side_count = t->h_ctrl->side_count;
     const uint64_t total = t->h_ctrl->size + (side ? 1 : 0);
     *n_out = total;
     if (cap == 0 || total == 0) return OXG_OK;
-    uint64_t *d_keys = nullptr, *d_vals = nullptr, live = 0;
-    TRY(export_device(t, &d_keys, &d_vals, &live));
-    std::vector<uint64_t> hk(live + 1), hv(live + 1);
-    if (live) {
-        CU(cudaMemcpy(hk.data(), d_keys, live * 8, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(hv.data(), d_vals, live * 8, cudaMemcpyDeviceToHost));
+    uint64_t max_count = 0;
+    if (sort_mode == 2) {
+        oxg_stats st;
+        TRY(run_stats(t, false, &st, nullptr));
+        max_count = st.max;
     }
-    CU(cudaFree(d_keys));
-    CU(cudaFree(d_vals));
+    uint64_t live = 0;
+    TRY(export_device(t, &live));
     uint64_t n = live;
-    if (side) { hk[n] = kEmpty; hv[n] = t->h_ctrl->side_count; ++n; }
-    if (sort_mode != 0) {
-        std::vector<uint64_t> order(n);
-        for (uint64_t i = 0; i < n; ++i) order[i] = i;
-        if (sort_mode == 1) std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hk[a] < hk[b]; });
-        else std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hv[a] != hv[b] ? hv[a] < hv[b] : hk[a] < hk[b]; });
-        for (uint64_t i = 0; i < std::min(n, cap); ++i) { if (keys) keys[i] = hk[order[i]]; if (vals) vals[i] = hv[order[i]]; }
-    } else {
-        for (uint64_t i = 0; i < std::min(n, cap); ++i) { if (keys) keys[i] = hk[i]; if (vals) vals[i] = hv[i]; }
+    if (side) {  // the out-of-band key 2^64-1 lives outside the slot array: it joins the pairs here
+        const uint64_t kv[2] = {kEmpty, side_count};
+        CU(cudaMemcpyAsync(c->d_exp_k[0] + n, &kv[0], 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_exp_v[0] + n, &kv[1], 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        ++n;
     }
+    int which = 0;
+    if (sort_mode != 0) TRY(sort_pairs_device(c, n, sort_mode, max_count, &which));
+    TRY(download(c, keys, c->d_exp_k[which], std::min(n, cap)));
+    TRY(download(c, vals, c->d_exp_v[which], std::min(n, cap)));
+    CU(cudaStreamSynchronize(c->stream));
     return OXG_OK;
 }
 

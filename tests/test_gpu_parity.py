@@ -467,3 +467,24 @@ def test_merge(capi):
     assert a.merge(b) == oa.add(ob)
     assert_same_table(a, oa)
     assert_same_table(b, ob)
+
+
+def test_export_sorted_on_the_device(capi):
+    # dump(sortkeys) / dump(sortcounts) (src/lib.rs:330-381): LSD radix sort on the device; many
+    # tiles, counts above one byte, keys 0 and 2^64-1 (the latter lives outside the slot array)
+    bases = synth_reads(120_000, 150, 60_000, seed=5, sub_ppm=3000)  # ~300x coverage + error singletons
+    offs = uniform_offsets(120_000, 150)
+    t = capi.Table(21)
+    t.consume_batch(bases, offs)
+    t.count_hashes(np.array([0, 0, 2**64 - 1, 2**64 - 1, 2**64 - 1, 7], dtype=np.uint64))
+    k0, v0 = t.export(0)
+    assert len(k0) == len(t) > 100_000 and v0.max() > 300
+    k0b, v0b = t.export(0)
+    assert np.array_equal(k0, k0b) and np.array_equal(v0, v0b)  # slot order is stable between calls
+    k1, v1 = t.export(1)
+    order = np.argsort(k0, kind="stable")
+    assert np.array_equal(k1, k0[order]) and np.array_equal(v1, v0[order])
+    assert k1[0] == 0 and v1[0] == 2 and k1[-1] == 2**64 - 1 and v1[-1] == 3
+    k2, v2 = t.export(2)
+    order = np.lexsort((k0, v0))  # by count, then by hash
+    assert np.array_equal(k2, k0[order]) and np.array_equal(v2, v0[order])
