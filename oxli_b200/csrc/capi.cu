@@ -617,7 +617,7 @@ double sketch_estimate(const uint32_t *regs) {
 
 // Before pass B: fold the group's hashes into the table's sketch and make room for what the
 // table will hold afterwards -- unless the caller's hint still covers it.  `src` as for pass B.
-oxg_status presize_for_group(oxg_table *t, const PartPlan &pl, const AggSource *src, int n_src, cudaStream_t stream) {
+oxg_status presize_for_group(oxg_table *t, const PartPlan &pl, const AggSource *src, int n_src, cudaStream_t stream, double headroom = 1.0) {
     DeviceCtx *c = t->ctx;
     if (!t->d_sketch) {
         CU(cudaMalloc(&t->d_sketch, kSketchRegs * 4));
@@ -636,7 +636,7 @@ oxg_status presize_for_group(oxg_table *t, const PartPlan &pl, const AggSource *
     CU(cudaMemcpyAsync(t->h_sketch, t->d_sketch, kSketchRegs * 4, cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
     const uint64_t unseen = t->size > t->sketch_covers ? t->size - t->sketch_covers : 0;  // keys that came in another way
-    const uint64_t expect = (uint64_t)(sketch_estimate(t->h_sketch) * 1.04) + unseen + 1024;  // three standard errors
+    const uint64_t expect = (uint64_t)(sketch_estimate(t->h_sketch) * 1.04 * headroom) + unseen + 1024;  // three standard errors
     if (expect * 10 > t->cap * 7) TRY(grow_to_fit(t, expect));
     return OXG_OK;
 }
