@@ -510,8 +510,10 @@ oxg_status plan_partitioned(oxg_table *t, uint64_t span, uint64_t n_tiles, int n
     while (sq * sq < fair) ++sq;
     pl.frag_cap = (uint32_t)((fair + fair / 2 + 4 * sq + line + line - 1) & ~(line - 1));
     pl.spill_cap = span;
+    // work items of pass B = partitions x groups: enough of them (four per SM) that the CTAs finish
+    // together -- 256 partitions of a shard on 148 SMs would otherwise be two uneven waves
     const uint32_t forced_groups = g_groups_override.load();
-    pl.groups = forced_groups ? forced_groups : 1;
+    pl.groups = forced_groups ? forced_groups : std::max<uint32_t>(1, std::min<uint32_t>(8, (4u * (uint32_t)c->sms + pl.n_parts - 1) / pl.n_parts));
     if (pl.frag_entries() >> 32) return fail(OXG_ERR_INVALID, "internal: fragment buffer too large for one launch");
     *out = pl;
     return OXG_OK;
@@ -617,7 +619,8 @@ double sketch_estimate(const uint32_t *regs) {
 
 // Before pass B: fold the group's hashes into the table's sketch and make room for what the
 // table will hold afterwards -- unless the caller's hint still covers it.  `src` as for pass B.
-oxg_status presize_for_group(oxg_table *t, const PartPlan &pl, const AggSource *src, int n_src, cudaStream_t stream, double headroom = 1.0) {
+oxg_status presize_for_group(oxg_table *t, const PartPlan &pl, const AggSource *src, int n_src, cudaStream_t stream,
+                             uint64_t arrivals = 0, uint64_t rounds_left = 1) {
     DeviceCtx *c = t->ctx;
     if (!t->d_sketch) {
         CU(cudaMalloc(&t->d_sketch, kSketchRegs * 4));
@@ -636,7 +639,22 @@ oxg_status presize_for_group(oxg_table *t, const PartPlan &pl, const AggSource *
     CU(cudaMemcpyAsync(t->h_sketch, t->d_sketch, kSketchRegs * 4, cudaMemcpyDeviceToHost, stream));
     CU(cudaStreamSynchronize(stream));
     const uint64_t unseen = t->size > t->sketch_covers ? t->size - t->sketch_covers : 0;  // keys that came in another way
-    const uint64_t expect = (uint64_t)(sketch_estimate(t->h_sketch) * 1.04 * headroom) + unseen + 1024;  // three standard errors
+    const double est = sketch_estimate(t->h_sketch);
+    // sharded tables call this in the first round only, with more rounds of the same size to come:
+    // where nearly everything that arrives is new (a quarter or more), room for half that rate over
+    // the whole batch, in one step (the rate falls as coverage builds up); else for the rounds in
+    // flight before the host monitor catches up
+    double headroom = 1.0;
+    if (rounds_left > 1) headroom = est * 4 >= (double)arrivals ? std::max(4.0, 0.5 * (double)rounds_left) : (double)std::min<uint64_t>(4, rounds_left);
+    uint64_t expect = (uint64_t)(est * 1.04 * headroom) + unseen + 1024;  // 1.04: three standard errors
+    if (headroom > 4.0) {  // a guess that size must not cost more than half of what is free
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        while (headroom > 4.0 && std::max(capacity_for_keys(expect), pow2_at_least(expect * 2)) * 16 > free_b / 2) {
+            headroom /= 2;
+            expect = (uint64_t)(est * 1.04 * std::max(headroom, 4.0)) + unseen + 1024;
+        }
+    }
     if (expect * 10 > t->cap * 7) TRY(grow_to_fit(t, expect));
     return OXG_OK;
 }
