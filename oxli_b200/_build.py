@@ -16,6 +16,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC",
 ]
+NVCC_FLAGS += os.environ.get("OXLI_B200_NVCC_FLAGS", "").split()  # experiments: -DOXG_SCAT_THREADS=..., ...
 OBJ = os.path.join(HERE, "_obj")
 
 

@@ -34,7 +34,7 @@ constexpr int kAggThreadsDefault = 768;              // one CTA per SM; 85 regis
                                                      // prefetched block of hashes out of local memory
 constexpr int kLocalBits = 14;
 constexpr uint32_t kLocalSlots = 1u << kLocalBits;  // 16384 x (8-byte key + 4-byte count) = 192 KB
-constexpr int kLocalProbe = 4;                      // buckets of two slots examined before bypassing
+constexpr int kLocalProbe = 2;                      // buckets of four slots examined before bypassing
 constexpr uint32_t kSpillSlice = 1u << 16;          // spill-list entries per work item
 constexpr int kMaxSources = 16;
 constexpr uint32_t kAggMaxFrags = 296 * kMaxSources;  // fragments of one partition: pass A CTAs x sources
@@ -110,24 +110,32 @@ __global__ void __launch_bounds__(512) sketch_kernel(const AggParams p, uint32_t
 inline size_t aggregate_smem_bytes() { return (size_t)kLocalSlots * 12 + (size_t)kAggMaxFrags * 4; }
 
 // One occurrence of h into the shared-memory table.  false = neighbourhood full, bypass.
-// Slots only ever go from empty to a key, so a stale "empty" is caught by the CAS and a stale
-// "other key" cannot happen; equal keys racing for a slot agree on it through the CAS result.
-__device__ __forceinline__ bool local_count(uint64_t *lk, uint32_t *ld, uint64_t h, uint32_t idx) {
-    uint32_t b = idx & ~1u;
+// Buckets of four slots (two 128-bit shared loads): at the loads this table runs at, a key sits in
+// its home bucket 99 times out of 100, so the probe loop almost never takes a second, divergent
+// turn (with two-slot buckets it did for one warp step in two, and pass B took 13.8 instead of
+// 9.4 ms per C2 step at twice the load).  Slots only ever go from empty to a key, so a stale
+// "empty" is caught by the CAS and a stale "other key" cannot happen; equal keys racing for a slot
+// agree on it through the CAS result.  A key lives in the first bucket of its probe sequence that
+// had a free slot when it came, and buckets never empty, so a lookup that walks past full buckets
+// finds it.
+__device__ __forceinline__ bool local_count(uint64_t *lk, uint32_t *ld, uint64_t h, uint32_t bucket) {
+    uint32_t b = bucket << 2;
 #pragma unroll 1
     for (int pr = 0; pr < kLocalProbe; ++pr) {
-        const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(lk + b);
-        if (kk.x == h) { atomicAdd(ld + b, 1u); return true; }
-        if (kk.y == h) { atomicAdd(ld + b + 1, 1u); return true; }
-        if (kk.x == kEmpty) {
-            const uint64_t old = atomicCAS((unsigned long long *)(lk + b), (unsigned long long)kEmpty, (unsigned long long)h);
-            if (old == kEmpty || old == h) { atomicAdd(ld + b, 1u); return true; }
+        const ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(lk + b);
+        const ulonglong2 k23 = *reinterpret_cast<const ulonglong2 *>(lk + b + 2);
+        const uint64_t kk[4] = {k01.x, k01.y, k23.x, k23.y};
+        int at = -1;
+#pragma unroll
+        for (int i = 3; i >= 0; --i) at = kk[i] == h ? i : at;
+        if (at >= 0) { atomicAdd(ld + b + at, 1u); return true; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (kk[i] != kEmpty) continue;
+            const uint64_t old = atomicCAS((unsigned long long *)(lk + b + i), (unsigned long long)kEmpty, (unsigned long long)h);
+            if (old == kEmpty || old == h) { atomicAdd(ld + b + i, 1u); return true; }
         }
-        if (kk.y == kEmpty) {
-            const uint64_t old = atomicCAS((unsigned long long *)(lk + b + 1), (unsigned long long)kEmpty, (unsigned long long)h);
-            if (old == kEmpty || old == h) { atomicAdd(ld + b + 1, 1u); return true; }
-        }
-        b = (b + 2) & (kLocalSlots - 1);
+        b = (b + 4) & (kLocalSlots - 1);
     }
     return false;
 }
@@ -179,8 +187,8 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_kernel(const AggPara
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (!((live >> u) & 1u)) continue;
-                const uint32_t idx = (uint32_t)(((h[u] * kPhi) << p.part_bits) >> (64 - kLocalBits));
-                if (h[u] == kEmpty || !local_count(lk, ld, h[u], idx)) direct |= 1u << u;
+                const uint32_t bucket = (uint32_t)(((h[u] * kPhi) << p.part_bits) >> (64 - (kLocalBits - 2)));
+                if (h[u] == kEmpty || !local_count(lk, ld, h[u], bucket)) direct |= 1u << u;
             }
         }
         if (direct) {  // two at a time: four sets of bucket registers do not fit the register budget
