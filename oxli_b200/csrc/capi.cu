@@ -464,8 +464,8 @@ bool use_partitioned(const oxg_table *t, uint64_t span) {
     return group >= 4 * keys;
 }
 
-// Partition count: about 4096 distinct keys per partition, so that the shared-memory table of
-// pass B (16384 slots in buckets of four) holds a partition's keys at load ~0.3 and duplicates
+// Partition count: 3072-6144 distinct keys per partition, so that the shared-memory table of
+// pass B (16384 slots in buckets of four) holds a partition's keys at load 0.2-0.4 and duplicates
 // meet there; at most max_parts, because pass A stages one line per destination in shared memory
 // (and keeps longer lines with fewer destinations).
 uint32_t choose_parts(const oxg_table *t, uint32_t max_parts) {
@@ -474,7 +474,7 @@ uint32_t choose_parts(const oxg_table *t, uint32_t max_parts) {
     const uint64_t est = std::max(t->size + t->last_new, t->hint_keys);
     if (est == 0) return std::min<uint32_t>(1024, max_parts);  // nothing known: the middle of the range
     uint64_t parts = 64;
-    while (parts < max_parts && parts * 4096 < est) parts <<= 1;
+    while (parts < max_parts && parts * 6144 < est) parts <<= 1;
     return (uint32_t)std::min<uint64_t>(parts, max_parts);
 }
 
