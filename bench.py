@@ -165,7 +165,7 @@ def run_reference(a, rank: int, world: int):
 
     w = workload(a, world)
     cores = os.cpu_count() or 1
-    n = min(w["reads_total"], max(a.cpu_sample_reads, 50_000 * cores))
+    n = min(w["reads_total"], max(a.cpu_sample_reads, 20_000 * cores))  # a second or two of CPU work per step
     bases = synth_reads(n, w["read_len"], w["genome_total"], w["seed"], sub_ppm=w["sub_ppm"], n_ppm=w["n_ppm"])
     offs = uniform_offsets(n, w["read_len"])
     times, total = [], 0

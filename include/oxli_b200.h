@@ -83,12 +83,16 @@ oxg_status oxg_hash_windows(oxg_table *t, const uint8_t *seq, uint64_t len, uint
  *                  "bad k-mer encountered at position {n}").
  * *total_counted = k-mers added to the table (valid windows whose hash is 0 are
  * skipped and not counted, src/lib.rs:589).  err_read = -1 when no error.
- * The host variant streams the buffer to the GPU in chunks with
- * double-buffered cudaMemcpyAsync. */
+ * The host variant streams the buffer to the GPU in 64 MiB chunks through a ring of
+ * four staging buffers (cudaMemcpyAsync on a copy stream, fed by a producer thread, which
+ * also checks that the offsets are non-decreasing: on OXG_ERR_INVALID for that reason the
+ * table may already hold the reads of earlier chunks). */
 oxg_status oxg_consume_batch(oxg_table *t, const uint8_t *bases, const uint64_t *offsets,
                              uint64_t n_reads, int skip_bad, uint64_t *total_counted,
                              int64_t *err_read, uint64_t *err_pos);
-/* same, inputs already resident in the table's HBM */
+/* same, inputs already resident in the table's HBM: d_bases 16-byte aligned, d_offsets[0]
+ * must be 0 (the batch is the bytes [0, total_bases)), offsets non-decreasing -- device
+ * arrays are not validated */
 oxg_status oxg_consume_batch_device(oxg_table *t, const uint8_t *d_bases, const uint64_t *d_offsets,
                                     uint64_t n_reads, uint64_t total_bases, int skip_bad,
                                     uint64_t *total_counted, int64_t *err_read,
