@@ -696,7 +696,7 @@ oxg_status flush_pending(oxg_table *t, uint64_t *counted) {
         // the call will bring them at no more than this rate: make the room now, in one step,
         // rather than by doubling under load.  0.6: the rate of a read set falls as coverage builds
         // up (C3-shaped input: 0.39 new keys per window in the first group, 0.22 over the whole set).
-        if (made * 4 >= t->pend.windows && t->part_budget) {
+        if (made * 4 >= t->pend.windows && t->part_budget && t->size * 20 >= t->cap * 7) {  // (only a table that is filling up)
             const uint64_t more = (uint64_t)((double)made / (double)t->pend.windows * 0.6 * (double)t->part_budget);
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
@@ -1371,11 +1371,43 @@ oxg_status oxg_erase_hashes(oxg_table *t, const uint64_t *hashes, uint64_t n, ui
     TRY(ensure_io(c, n));
     memcpy(c->h_io, hashes, n * 8);
     CU(cudaMemcpyAsync(c->d_io, c->h_io, n * 8, cudaMemcpyHostToDevice, c->stream));
-    erase_hashes_kernel<<<1, 32, 0, c->stream>>>(view_of(t, false), c->d_io, n);
+    if (n < 256) {
+        // the reference's usage: one key per call (drop / drop_hash, src/lib.rs:197-224)
+        erase_hashes_kernel<<<1, 32, 0, c->stream>>>(view_of(t, false), c->d_io, n);
+        LAUNCHED();
+        CU(cudaGetLastError());
+        TRY(pull_ctrl(t));
+        if (n_removed) *n_removed = t->h_ctrl->scratch[0];
+        return OXG_OK;
+    }
+    // a list: mark in parallel, rebuild once
+    TRY(pull_ctrl(t));
+    uint32_t *d_doomed = nullptr;
+    const uint64_t words = (t->cap + 31) / 32;
+    CU(cudaMalloc(&d_doomed, words * 4));
+    CU(cudaMemsetAsync(d_doomed, 0, words * 4, c->stream));
+    TRY(zero_ctrl_fields(t, kFieldScratch, 1));
+    erase_mark_kernel<<<grid_for(c, n, kOpThreads, 16), kOpThreads, 0, c->stream>>>(view_of(t, false), c->d_io, n, d_doomed);
+    LAUNCHED();
+    ulonglong2 *fresh = nullptr;
+    TRY(alloc_slots(c, t->cap, &fresh, t->pooled));
+    ulonglong2 *old = t->slots;
+    t->slots = fresh;
+    erase_rebuild_kernel<<<grid_for(c, t->cap, kOpThreads, 16), kOpThreads, 0, c->stream>>>(old, t->cap, view_of(t, false), d_doomed);
     LAUNCHED();
     CU(cudaGetLastError());
     TRY(pull_ctrl(t));
-    if (n_removed) *n_removed = t->h_ctrl->scratch[0];
+    if (t->pooled) CU(cudaFreeAsync(old, c->stream)); else CU(cudaFree(old));
+    CU(cudaFree(d_doomed));
+    uint64_t removed = t->h_ctrl->scratch[0];
+    t->h_ctrl->size -= removed;
+    if (t->h_ctrl->side_present && std::find(hashes, hashes + n, kEmpty) != hashes + n) {
+        t->h_ctrl->side_present = 0; t->h_ctrl->side_count = 0; ++removed;
+    }
+    t->size = t->h_ctrl->size;
+    CU(cudaMemcpyAsync(t->d_ctrl, t->h_ctrl, offsetof(Ctrl, counted), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (n_removed) *n_removed = removed;
     return OXG_OK;
 }
 

@@ -176,6 +176,32 @@ __global__ void erase_hashes_kernel(TableView t, const uint64_t *__restrict__ ha
     t.ctrl->scratch[0] = removed;
 }
 
+// Bulk form of drop_hash: mark the slots of the listed keys in a bitmap (one bit per slot; a key
+// listed twice is marked once), then rebuild without them (erase_rebuild_kernel) -- the
+// single-thread kernel above is for the reference's one-key calls, this one for lists.
+// scratch[0] += keys found.
+__global__ void erase_mark_kernel(TableView t, const uint64_t *__restrict__ hashes, uint64_t n, uint32_t *__restrict__ doomed) {
+    uint64_t found = 0;
+    for (uint64_t q = gtid(); q < n; q += gstride()) {
+        const uint64_t key = hashes[q];
+        if (key == kEmpty) continue;  // the out-of-band key is handled on the host
+        const int64_t f = table_find(t, key);
+        if (f < 0) continue;
+        const uint32_t bit = 1u << (f & 31);
+        if (!(atomicOr(&doomed[f >> 5], bit) & bit)) ++found;
+    }
+    found = warp_sum(found);
+    if ((threadIdx.x & 31) == 0 && found) atomicAdd((unsigned long long *)&t.ctrl->scratch[0], (unsigned long long)found);
+}
+
+__global__ void erase_rebuild_kernel(const ulonglong2 *__restrict__ old_slots, uint64_t old_cap, TableView nt, const uint32_t *__restrict__ doomed) {
+    for (uint64_t i = gtid(); i < old_cap; i += gstride()) {
+        const ulonglong2 s = old_slots[i];
+        if (s.x == kEmpty || ((doomed[i >> 5] >> (i & 31)) & 1u)) continue;
+        table_add(nt, s.x, s.y, false);
+    }
+}
+
 // growth: re-insert every live entry of the old slot array
 __global__ void rehash_kernel(const ulonglong2 *__restrict__ old_slots, uint64_t old_cap, TableView nt) {
     for (uint64_t i = gtid(); i < old_cap; i += gstride()) {

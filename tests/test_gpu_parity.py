@@ -388,6 +388,15 @@ def test_hash_level_ops(capi):
     for h in victims:
         ora.drop_hash(h)
     assert_same_table(t, ora)
+    # a list long enough for the mark-and-rebuild path: duplicates, missing keys, the out-of-band key
+    t.set_hash(2**64 - 1, 3); ora.set_hash(2**64 - 1, 3)
+    bulk = [int(x) for x in keys[200:2200]] + [int(x) for x in keys[300:400]] + [2**64 - 1, 5, 123456789]
+    want_removed = sum(1 for h in set(bulk) if ora.contains(h))
+    assert t.erase_hashes(bulk) == want_removed
+    for h in bulk:
+        ora.drop_hash(h)
+    assert_same_table(t, ora)
+    assert list(t.get_hashes(probe)) == [ora.get_hash(int(h)) for h in probe]
     # mincut / maxcut
     assert t.cut(0, 3) == ora.mincut(3)
     assert_same_table(t, ora)
