@@ -165,7 +165,10 @@ def run_reference(a, rank: int, world: int):
 
     w = workload(a, world)
     cores = os.cpu_count() or 1
-    n = min(w["reads_total"], max(a.cpu_sample_reads, 20_000 * cores))  # a second or two of CPU work per step
+    # a few seconds of CPU work per step: on C2 (every key seen hundreds of times) the threads' tables stay
+    # small and the sample can grow with the cores; on C3 nearly every k-mer is a new key, the port's
+    # per-thread tables and their merge (KmerCountTable.add's role) cost 10x more per k-mer
+    n = min(w["reads_total"], a.cpu_sample_reads if w["sub_ppm"] else max(a.cpu_sample_reads, 20_000 * cores))
     bases = synth_reads(n, w["read_len"], w["genome_total"], w["seed"], sub_ppm=w["sub_ppm"], n_ppm=w["n_ppm"])
     offs = uniform_offsets(n, w["read_len"])
     times, total = [], 0
