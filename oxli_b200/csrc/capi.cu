@@ -88,7 +88,11 @@ static const uint64_t kChunkBytes = [] {
     }
     return (uint64_t)mb << 20;
 }();
-constexpr uint64_t kLaunchWindows = 64ull << 20;  // windows per consume launch (bounds the overflow list)
+static const uint64_t kLaunchWindows = [] {  // windows per consume launch (bounds the overflow list); OXLI_B200_LAUNCH_MW for experiments
+    const char *e = getenv("OXLI_B200_LAUNCH_MW");
+    const long v = e && *e ? atol(e) : 64;
+    return (uint64_t)(v >= 1 && v <= 1024 ? v : 64) << 20;
+}();
 constexpr uint64_t kSmallBatch = 1ull << 20;      // below this, reserve for the worst case up front
 constexpr uint64_t kMinCap = 1024;
 // Launches of at least this many windows go through the partitioned pipeline (pass A scatter,
@@ -104,7 +108,7 @@ static std::atomic<int> g_pipeline{[] {
 static std::atomic<uint32_t> g_parts_override{(uint32_t)env_int("OXLI_B200_PARTS", 0)};    // 0 = from the table size
 // pass A launches whose fragments pass B takes together (more duplicates per key meet in one
 // aggregation, one merge instead of several); 1 = pass B after every pass A
-static std::atomic<uint32_t> g_accumulate{(uint32_t)std::max(1, std::min(16, env_int("OXLI_B200_ACCUMULATE", 4)))};
+static std::atomic<uint32_t> g_accumulate{(uint32_t)std::max(1, std::min(16, env_int("OXLI_B200_ACCUMULATE", 8)))};
 static std::atomic<uint32_t> g_groups_override{(uint32_t)env_int("OXLI_B200_GROUPS", 0)};  // 0 = default
 constexpr int kStageBufs = 4;  // host batches: chunks in flight between the copy stream and the kernels
 
@@ -281,6 +285,7 @@ struct oxg_table {
         uint64_t windows = 0, planned = 0;
     } pend;
     uint64_t part_budget = 0;  // windows the running consume call still has to go (0 = unknown)
+    uint32_t group_cap = 0;    // != 0: at most this many pass A launches per pass B in the running call
     // HyperLogLog sketch of the keys that came in through the partitioned pipeline (aggregate.cuh)
     uint32_t *d_sketch = nullptr;
     uint32_t *h_sketch = nullptr;  // pinned
@@ -443,6 +448,13 @@ oxg_status launch_consume(oxg_table *t, const ConsumeParams &p) {
 
 // ---- partitioned pipeline: pass A (hash + scatter) and pass B (aggregate + merge) -----------
 
+// pass A launches per pass B: eight when the reads are resident (pass B 8.0 instead of 9.2 ms per C2
+// step), four when they stream in from the host (the last group's pass B is the tail of the call)
+uint32_t group_launches(const oxg_table *t) {
+    const uint32_t g = g_accumulate.load();
+    return t->group_cap ? std::min(g, t->group_cap) : g;
+}
+
 // Which pipeline a counting launch of `span` windows takes.  Measured on one B200
 // (profiles/r2_pipeline_choice.txt): the partitioned pipeline matches the fused kernel on a hot
 // table (C2: 31.4 vs 31.0 ms per step), is 30x faster on low-complexity input (every window the
@@ -460,7 +472,7 @@ bool use_partitioned(const oxg_table *t, uint64_t span) {
     if (t->pend.active) return true;  // a group in flight is completed the way it began
     const uint64_t keys = std::max(t->size + t->last_new, t->hint_keys);
     if (keys == 0) return true;
-    const uint64_t group = std::min<uint64_t>(std::max<uint64_t>(t->part_budget, span), (uint64_t)g_accumulate.load() * kLaunchWindows);
+    const uint64_t group = std::min<uint64_t>(std::max<uint64_t>(t->part_budget, span), (uint64_t)group_launches(t) * kLaunchWindows);
     return group >= 4 * keys;
 }
 
@@ -764,7 +776,7 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
             const uint64_t span = hi - lo;
             if (t->pend.active && t->pend.windows + span > t->pend.planned) TRY(flush_pending(t, counted));
             if (!t->pend.active) {
-                const uint64_t planned = std::min<uint64_t>(std::max<uint64_t>(t->part_budget, span), (uint64_t)g_accumulate.load() * kLaunchWindows);
+                const uint64_t planned = std::min<uint64_t>(std::max<uint64_t>(t->part_budget, span), (uint64_t)group_launches(t) * kLaunchWindows);
                 TRY(plan_partitioned(t, planned, planned / tw + 1, 1, 0, &t->pend.pl));
                 TRY(ensure_part_buffers(c, t->pend.pl));
                 t->pend.active = true; t->pend.launches = 0; t->pend.windows = 0; t->pend.planned = planned;
@@ -773,7 +785,7 @@ oxg_status run_span(oxg_table *t, int mode, const uint8_t *d_bases, uint64_t g0,
             TRY(launch_part_a(t, p, t->pend.pl, c->d_frag, c->d_frag_cnt, c->d_spill, c->d_spill_n, c->stream, t->pend.launches > 0));
             t->pend.launches += 1; t->pend.windows += span;
             t->part_budget = t->part_budget > span ? t->part_budget - span : 0;
-            if (t->pend.launches >= g_accumulate.load() || t->pend.windows >= t->pend.planned) TRY(flush_pending(t, counted));
+            if (t->pend.launches >= group_launches(t) || t->pend.windows >= t->pend.planned) TRY(flush_pending(t, counted));
             lo = hi;
             continue;
         }
@@ -816,6 +828,7 @@ oxg_status consume_resident(oxg_table *t, const uint8_t *d_bases, const uint64_t
     t->last_ms = 0.f; t->last_ms_a = 0.f; t->last_ms_b = 0.f; t->last_launches = 0;
     const uint64_t n_win = total >= k ? total - k + 1 : 0;
     t->part_budget = n_win;
+    t->group_cap = 0;
     oxg_status ret = OXG_OK;
     if (skip_bad || n_win == 0) {
         TRY(run_span(t, kModeCount, d_bases, 0, 0, n_win, total, d_offsets, n_reads + 1, nullptr, &counted));
@@ -1224,6 +1237,7 @@ oxg_status oxg_consume_batch(oxg_table *t, const uint8_t *bases, const uint64_t 
     t->last_ms = 0.f; t->last_ms_a = 0.f; t->last_ms_b = 0.f; t->last_launches = 0;
     if (n_win == 0) return OXG_OK;
     t->part_budget = n_win;
+    t->group_cap = 4;
     cudaPointerAttributes attr{};
     bool pinned = cudaPointerGetAttributes(&attr, bases) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
@@ -1259,6 +1273,7 @@ oxg_status oxg_consume_batch(oxg_table *t, const uint8_t *bases, const uint64_t 
     }
     if (ret == OXG_OK) TRY(flush_pending(t, &counted));
     t->part_budget = 0;
+    t->group_cap = 0;
     if (total_counted) *total_counted = counted;
     return ret;
 }
