@@ -49,7 +49,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     one shared library."""
     from concurrent.futures import ThreadPoolExecutor
 
-    srcs = _sources((".cu", ".cuh", ".h"))
+    srcs = _sources((".cu", ".cuh", ".h", ".inc"))
     if not force and not _stale(LIB, srcs):
         return LIB  # up to date (the objects do not travel to the GPU box; the library does)
     os.makedirs(OBJ, exist_ok=True)

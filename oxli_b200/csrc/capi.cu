@@ -710,11 +710,13 @@ oxg_status flush_pending(oxg_table *t, uint64_t *counted) {
         // up (C3-shaped input: 0.39 new keys per window in the first group, 0.22 over the whole set).
         if (made * 4 >= t->pend.windows && t->part_budget && t->size * 20 >= t->cap * 7) {  // (only a table that is filling up)
             const uint64_t more = (uint64_t)((double)made / (double)t->pend.windows * 0.6 * (double)t->part_budget);
-            size_t free_b = 0, total_b = 0;
-            CU(cudaMemGetInfo(&free_b, &total_b));
             const uint64_t want = t->size + more;
             const uint64_t cap_want = std::max(capacity_for_keys(want), pow2_at_least(want * 2));
-            if (cap_want > t->cap && cap_want * 16 < free_b / 2) TRY(grow_to_fit(t, want));
+            if (cap_want > t->cap) {  // (cudaMemGetInfo is a slow driver call, 10-150 ms at times: only when there is a question)
+                size_t free_b = 0, total_b = 0;
+                CU(cudaMemGetInfo(&free_b, &total_b));
+                if (cap_want * 16 < free_b / 2) TRY(grow_to_fit(t, want));
+            }
         }
     }
     return OXG_OK;
