@@ -56,6 +56,7 @@ struct AggParams {
     uint32_t frag_cap;
     uint32_t part_bits;   // log2(n_parts)
     uint32_t groups;      // work items per partition: item (part, g) takes the fragments f with f % groups == g
+                          // (aggregate_groups: few with the cache on, some thousands of items in all with it off)
     uint32_t use_cache;   // 0: nothing to pre-reduce (nearly every key new): update the table directly
     uint64_t spill_cap;
     int owner_shift, self_rank, n_ranks;  // owner(h) = h >> owner_shift, for the spill lists
@@ -245,20 +246,35 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_kernel(const AggPara
                 s_cnt[f] = min(__ldg(p.src[s].frag_cnt + dest * p.n_ctas + (f - s * p.n_ctas)), p.frag_cap);
             }
             __syncthreads();
-            const uint64_t *cur = nullptr;  // rest of the fragment in hand
+            // Work inside the item: whole fragments per warp when the item has plenty (eight per warp
+            // or more: the warps stay level anyway, and a warp streams its fragment front to back);
+            // else in blocks of kBlk hashes, block b of every fragment of the item before block b + 1
+            // of any -- a load is still 1 KB in one piece, and no warp idles however few fragments
+            // there are (with two fragments per item, 22 of 24 warps had nothing to do).
+            const uint32_t n_mine = g < n_frag ? (n_frag - g + p.groups - 1) / p.groups : 0;  // fragments g, g + groups, ...
+            const bool by_block = n_mine < 8u * (kAggThreads / 32);
+            const uint32_t n_units = by_block ? n_mine * ((p.frag_cap + kBlk - 1) / kBlk) : n_mine;
+            const uint64_t *cur = nullptr;  // (whole fragments) rest of the fragment in hand
             uint32_t left = 0;
             auto next_blk = [&](const uint64_t *&ptr, uint32_t &n) {  // warp-uniform; n = 0: nothing left
-                while (left == 0) {
-                    uint32_t f = 0;
-                    if (lane == 0) f = atomicAdd(&s_next, 1u);
-                    f = g + __shfl_sync(0xffffffffu, f, 0) * p.groups;
-                    if (f >= n_frag) { n = 0; return; }
+                for (;;) {
+                    if (left) {
+                        ptr = cur; n = min(left, kBlk);
+                        cur += n; left -= n;
+                        return;
+                    }
+                    uint32_t u = 0;
+                    if (lane == 0) u = atomicAdd(&s_next, 1u);
+                    u = __shfl_sync(0xffffffffu, u, 0);
+                    if (u >= n_units) { n = 0; return; }
+                    const uint32_t b = by_block ? u / n_mine : 0u, f = g + (u - b * n_mine) * p.groups;
+                    const uint32_t have = s_cnt[f];
+                    if (b * kBlk >= have) continue;
                     const uint32_t s = f / p.n_ctas;
-                    left = s_cnt[f];
-                    cur = p.src[s].frag + (dest * p.n_ctas + (f - s * p.n_ctas)) * p.frag_cap;
+                    const uint64_t *at = p.src[s].frag + (dest * p.n_ctas + (f - s * p.n_ctas)) * p.frag_cap + b * kBlk;
+                    if (by_block) { ptr = at; n = min(have - b * kBlk, kBlk); return; }
+                    cur = at; left = have;
                 }
-                ptr = cur; n = min(left, kBlk);
-                cur += n; left -= n;
             };
             const uint64_t *ptr = nullptr, *ptr2 = nullptr;
             uint32_t n = 0, n2 = 0;

@@ -290,6 +290,7 @@ struct oxg_table {
     uint32_t *d_sketch = nullptr;
     uint32_t *h_sketch = nullptr;  // pinned
     uint64_t sketch_covers = 0;    // keys of the table the sketch has seen
+    uint64_t est_keys = 0;         // the sketch's last word on how many keys the table is about to hold
     uint64_t last_made = 0;        // keys the previous group of launches created
     uint64_t last_new = 0;   // keys created by the previous consume launch (growth look-ahead)
     float last_ms = 0.f;
@@ -456,24 +457,21 @@ uint32_t group_launches(const oxg_table *t) {
 }
 
 // Which pipeline a counting launch of `span` windows takes.  Measured on one B200
-// (profiles/r2_pipeline_choice.txt): the partitioned pipeline matches the fused kernel on a hot
-// table (C2: 31.4 vs 31.0 ms per step), is 30x faster on low-complexity input (every window the
-// same k-mer: the fused kernel's REDs all hit one address) and is slower when nearly every key
-// is new (C3-shaped: 11.3 vs 14.6 G k-mers/s -- nothing to pre-reduce, and the detour through
-// fragments is pure cost).  So: small launches stay fused; a group of launches is partitioned
-// when it brings at least four occurrences per key the table is known (or hinted) to hold, or
-// when nothing is known yet -- the first group of a new table pays at most the detour and tells.
+// (profiles/r2_pipeline_choice.txt): the partitioned pipeline matches or beats the fused kernel
+// everywhere but on small launches -- hot table (C2: 29.0 vs 31.0 ms per step), low-complexity
+// input (every window the same k-mer: 30x before the fused kernel learnt to pre-reduce a warp's
+// repeats, on a par since), and, with pass B updating the table directly from a few thousand work
+// items, input where nearly every key is new (C3-shaped, 273 M keys in 8 GiB: 65 vs 99 ms) -- there
+// the fused kernel's updates are random DRAM accesses issued between hashes, pass B's come
+// partition by partition.  Small launches stay fused: two kernels and a pass over fragments do
+// not pay below some millions of windows.
 bool use_partitioned(const oxg_table *t, uint64_t span) {
     if (!specialised_entry(t->k, kModePart)) return false;
     const int choice = g_pipeline.load();
     if (choice == 1) return false;
     if (choice == 2) return true;
-    if (span < kPartMinWindows) return false;
     if (t->pend.active) return true;  // a group in flight is completed the way it began
-    const uint64_t keys = std::max(t->size + t->last_new, t->hint_keys);
-    if (keys == 0) return true;
-    const uint64_t group = std::min<uint64_t>(std::max<uint64_t>(t->part_budget, span), (uint64_t)group_launches(t) * kLaunchWindows);
-    return group >= 4 * keys;
+    return span >= kPartMinWindows;
 }
 
 // Partition count: 3072-6144 distinct keys per partition, so that the shared-memory table of
@@ -583,11 +581,25 @@ oxg_status launch_aggregate(const AggParams &a, int grid, size_t smem, cudaStrea
     return OXG_OK;
 }
 
-// The shared-memory table of pass B pays when keys repeat inside what it is given: at least two
-// occurrences per key the table is known to hold (an empty table tells nothing: cache on).
-uint32_t use_cache_for(const oxg_table *t, uint64_t windows) {
-    const uint64_t keys = std::max(t->size, t->hint_keys);
-    return keys == 0 || windows >= 2 * keys ? 1u : 0u;
+// The shared-memory table of pass B pays when keys repeat inside what it is given -- at least two
+// occurrences per key the table holds, is hinted to hold or (sketch) is about to hold -- and a
+// partition's keys fit it: 16 Ki slots took 4.9 K keys per partition at 9.2 ms per C2 step and
+// 9.8 K at 19.6.  Nothing known at all (no hint, no sketch yet): on.
+static const int g_cache_override = env_int("OXLI_B200_AGG_CACHE", -1);  // experiments: 0 / 1 force it off / on
+uint32_t use_cache_for(const oxg_table *t, const PartPlan &pl, uint64_t windows) {
+    if (g_cache_override >= 0) return g_cache_override ? 1u : 0u;
+    const uint64_t keys = std::max(std::max(t->size, t->hint_keys), t->est_keys);
+    return keys == 0 || (windows >= 2 * keys && keys <= 8192ull * pl.n_parts) ? 1u : 0u;
+}
+
+// Work items per partition.  With the cache on, as few as keep the SMs level (the plan's: every
+// item empties and merges a cache).  With it off an item is just a share of the partition's
+// hashes, and 4-16 thousand items in all measured best (C3-shaped input, 1.6 G hashes into a
+// 8 GiB table, pass B per step: 1024 partitions x 1 / 3 / 12 / 25 / 50 / 148 items = 60.5 / 40.2 /
+// 39.0 / 41.7 / 48.5 / 74.0 ms; 256 x 37 / 148 = 37.9 / 43.9).
+uint32_t aggregate_groups(const PartPlan &pl, uint32_t use_cache) {
+    if (use_cache || g_groups_override.load()) return pl.groups;
+    return std::max<uint32_t>(pl.groups, std::min<uint32_t>(64, (8192 + pl.n_parts - 1) / pl.n_parts));
 }
 
 // pass B over n_src sources (one, this device's own pass A output, without sharding)
@@ -603,13 +615,14 @@ oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src,
     for (int s = 0; s < n_src; ++s) a.src[s] = src[s];
     a.n_src = n_src;
     a.n_parts = pl.n_parts; a.dest0 = (uint32_t)pl.self_rank * pl.n_parts; a.n_ctas = pl.grid_a;
-    a.frag_cap = pl.frag_cap; a.part_bits = pl.part_bits; a.groups = pl.groups; a.spill_cap = pl.spill_cap;
+    a.frag_cap = pl.frag_cap; a.part_bits = pl.part_bits; a.spill_cap = pl.spill_cap;
     a.owner_shift = pl.owner_shift; a.self_rank = pl.self_rank; a.n_ranks = pl.n_ranks;
     a.work_counter = (unsigned long long *)&t->d_ctrl->absorb_counter;
-    a.use_cache = use_cache_for(t, windows);
+    a.use_cache = use_cache_for(t, pl, windows);
+    a.groups = aggregate_groups(pl, a.use_cache);
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_fn(), agg_threads(), smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const uint64_t items = (uint64_t)pl.n_parts * pl.groups;
+    const uint64_t items = (uint64_t)pl.n_parts * a.groups;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(items, (uint64_t)c->sms * per_sm));
     TRY(launch_aggregate(a, grid, smem, c->stream));
     LAUNCHED();
@@ -652,6 +665,7 @@ oxg_status presize_for_group(oxg_table *t, const PartPlan &pl, const AggSource *
     CU(cudaStreamSynchronize(stream));
     const uint64_t unseen = t->size > t->sketch_covers ? t->size - t->sketch_covers : 0;  // keys that came in another way
     const double est = sketch_estimate(t->h_sketch);
+    t->est_keys = (uint64_t)est + unseen;
     // sharded tables call this in the first round only, with more rounds of the same size to come:
     // where nearly everything that arrives is new (a quarter or more), room for half that rate over
     // the whole batch, in one step (the rate falls as coverage builds up); else for the rounds in
@@ -937,6 +951,7 @@ oxg_status oxg_table_clear(oxg_table *t) {
     CU(cudaMemsetAsync(t->d_ctrl, 0, sizeof(Ctrl), c->stream));
     if (t->d_sketch) CU(cudaMemsetAsync(t->d_sketch, 0, kSketchRegs * 4, c->stream));
     t->sketch_covers = 0;
+    t->est_keys = 0;
     t->last_made = 0;
     t->size = 0;
     t->last_new = 0;
