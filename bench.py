@@ -61,6 +61,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--round-mw", type=int, default=256, help="sharded table: Mi windows per round of a device-resident batch "
+                    "(the library's default is 64: see DESIGN.md section 6)")
     ap.add_argument("--table-hint", type=int, default=-1, help="expected distinct k-mers (-1: genome length for c2, none for c3)")
     return ap.parse_args()
 
@@ -448,7 +450,8 @@ def run_sharded(a, rank: int, world: int, local: int):
     offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(L)
     capi.h2d(d_offs, offs, local)
     hint = a.table_hint if a.table_hint > 0 else 0
-    st_table = ShardedTable(k, rank, world, device=local, exchange=exchange, capacity_hint=hint // world if hint else 0)
+    st_table = ShardedTable(k, rank, world, device=local, exchange=exchange, capacity_hint=hint // world if hint else 0,
+                            round_windows=a.round_mw << 20)
     shard = st_table.engine
     info = shard.info()
     counted = None

@@ -594,12 +594,14 @@ uint32_t use_cache_for(const oxg_table *t, const PartPlan &pl, uint64_t windows)
 
 // Work items per partition.  With the cache on, as few as keep the SMs level (the plan's: every
 // item empties and merges a cache).  With it off an item is just a share of the partition's
-// hashes, and 4-16 thousand items in all measured best (C3-shaped input, 1.6 G hashes into a
-// 8 GiB table, pass B per step: 1024 partitions x 1 / 3 / 12 / 25 / 50 / 148 items = 60.5 / 40.2 /
-// 39.0 / 41.7 / 48.5 / 74.0 ms; 256 x 37 / 148 = 37.9 / 43.9).
-uint32_t aggregate_groups(const PartPlan &pl, uint32_t use_cache) {
+// hashes: some thousands of items of 40 thousand hashes or more measured best (C3-shaped input,
+// 8 GiB table, pass B over 512 Mi hashes at a time: 1024 partitions x 1 / 3 / 12 / 25 / 50 / 148
+// items = 60.5 / 40.2 / 39.0 / 41.7 / 48.5 / 74.0 ms per step; 256 x 37 / 148 = 37.9 / 43.9; a shard's
+// 1024 partitions over 64 Mi hashes at a time: x 3 / 8 / 16 = 86.7 / 94.5 / 120.5 ms per step).
+uint32_t aggregate_groups(const PartPlan &pl, uint32_t use_cache, uint64_t hashes) {
     if (use_cache || g_groups_override.load()) return pl.groups;
-    return std::max<uint32_t>(pl.groups, std::min<uint32_t>(64, (8192 + pl.n_parts - 1) / pl.n_parts));
+    const uint64_t items = std::max<uint64_t>(1, hashes / 40960);
+    return (uint32_t)std::max<uint64_t>(pl.groups, std::min<uint64_t>(64, (items + pl.n_parts - 1) / pl.n_parts));
 }
 
 // pass B over n_src sources (one, this device's own pass A output, without sharding)
@@ -619,7 +621,7 @@ oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src,
     a.owner_shift = pl.owner_shift; a.self_rank = pl.self_rank; a.n_ranks = pl.n_ranks;
     a.work_counter = (unsigned long long *)&t->d_ctrl->absorb_counter;
     a.use_cache = use_cache_for(t, pl, windows);
-    a.groups = aggregate_groups(pl, a.use_cache);
+    a.groups = aggregate_groups(pl, a.use_cache, windows);
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_fn(), agg_threads(), smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     const uint64_t items = (uint64_t)pl.n_parts * a.groups;

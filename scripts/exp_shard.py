@@ -35,8 +35,8 @@ def mx(x):
     return float(t.item())
 
 
-for name, rw, groups, hint in (("default", 0, 0, 0), ("groups=1", 0, 1, 0), ("round=16Mi", 16 << 20, 0, 0),
-                               ("round=256Mi", 256 << 20, 0, 0), ("hinted 400M/shard", 0, 0, 400_000_000)):
+for name, rw, groups, hint in (("default", 0, 0, 0), ("round=256Mi", 256 << 20, 0, 0), ("round=512Mi", 512 << 20, 0, 0),
+                               ("round=256Mi hinted 280M/shard", 256 << 20, 0, 280_000_000)):
     capi.set_pipeline("auto", 0, groups)
     t = ShardedTable(k, rank, world, device=local, exchange=exchange, round_windows=rw, capacity_hint=hint)
     ms = []

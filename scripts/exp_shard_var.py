@@ -43,7 +43,7 @@ def mx(x):
 if rank == 0:
     quota = open("/sys/fs/cgroup/cpu.max").read().strip() if os.path.exists("/sys/fs/cgroup/cpu.max") else "?"
     print(f"host: cpu_count {os.cpu_count()}, affinity {len(os.sched_getaffinity(0))}, cgroup cpu.max {quota}, load {os.getloadavg()}", flush=True)
-t = ShardedTable(k, rank, world, device=local, exchange=exchange)
+t = ShardedTable(k, rank, world, device=local, exchange=exchange, round_windows=int(os.environ.get('ROUND_MW', 0)) << 20)
 for _ in range(3):
     t.engine.table.clear()
     t.consume_batch_device(d_b, d_o, n, n * L, True)
