@@ -92,15 +92,17 @@ def measured_peak_gbs() -> tuple[float, str]:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs.  The poller is
+    started early (it needs some hundred ms to produce its first row, more when eight ranks start
+    one each) and rows are kept by arrival time: only those that came in between `with` entry and
+    exit count."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.rows, self.proc, self.index = [], None, index
-
-    def __enter__(self):
+        self.t_in = self.t_out = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -109,24 +111,34 @@ class ClockSampler:
             self.thread.start()
         except Exception:
             self.proc = None
+
+    def __enter__(self):
+        self.t_in = time.perf_counter()
         return self
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def __exit__(self, *exc):
+        self.t_out = time.perf_counter()
+        time.sleep(0.12)  # (a row that was being produced when the region ended)
+        self.close()
+
+    def close(self):
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+            self.proc = None
 
     def summary(self) -> dict:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t_in is not None and self.t_in <= t <= (self.t_out or t) + 0.12]
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for name, v in zip(names, r[4:8]):
@@ -304,12 +316,13 @@ def run_single(a, local: int):
         counted = total
         return table.last_consume_kernel_ms(), table.last_consume_pass_ms()
 
+    clocks = ClockSampler(dev)
     for _ in range(a.warmup):
         step_resident()
     table.sync()
     launches0 = int(capi.lib.oxg_launch_count())
     kernel_ms, kernel_launches, ms_a, ms_b = 0.0, 0, 0.0, 0.0
-    with ClockSampler(dev) as clocks:
+    with clocks:
         table.timer_start()
         t0 = time.perf_counter()
         for _ in range(a.steps):
@@ -464,12 +477,13 @@ def run_sharded(a, rank: int, world: int, local: int):
         counted = got
         return shard.last_ms()[0]
 
+    clocks = ClockSampler(local)
     for _ in range(a.warmup):
         step_resident()
     dist.barrier(); torch.cuda.synchronize()
     launches0 = int(capi.lib.oxg_launch_count())
     ev_ms = 0.0
-    with ClockSampler(local) as clocks:
+    with clocks:
         t0 = time.perf_counter()
         for _ in range(a.steps):
             ev_ms += step_resident()
