@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(512) sketch_kernel(const AggParams p, uint32_t
         if (regs[i]) atomicMax(&sketch[i], regs[i]);
 }
 
-inline size_t aggregate_smem_bytes() { return (size_t)kLocalSlots * 12 + (size_t)kAggMaxFrags * 4; }
+inline size_t aggregate_smem_bytes(bool cache = true) { return (cache ? (size_t)kLocalSlots * 12 : 0) + (size_t)kAggMaxFrags * 4; }
 
 // One occurrence of h into the shared-memory table.  false = neighbourhood full, bypass.
 // Buckets of four slots (two 128-bit shared loads): at the loads this table runs at, a key sits in
@@ -141,12 +141,16 @@ __device__ __forceinline__ bool local_count(uint64_t *lk, uint32_t *ld, uint64_t
     return false;
 }
 
-template <int kAggThreads>
+// kCache = false (p.use_cache == 0): no shared-memory table, every hash updates the table in HBM;
+// the registers the cache path needs go to twice as many table loads in flight per lane (this
+// variant is bound by the latency of those loads: 69 % of its stall samples are long-scoreboard,
+// profiles/r2_aggregate_direct_ncu_summary.txt).
+template <int kAggThreads, bool kCache>
 __global__ void __launch_bounds__(kAggThreads, 1) aggregate_kernel(const AggParams p) {
     extern __shared__ __align__(16) uint8_t agg_smem[];
     uint64_t *lk = reinterpret_cast<uint64_t *>(agg_smem);                    // keys
     uint32_t *ld = reinterpret_cast<uint32_t *>(agg_smem + kLocalSlots * 8);  // occurrences
-    uint32_t *s_cnt = ld + kLocalSlots;                                       // fill counts of the item's fragments
+    uint32_t *s_cnt = kCache ? ld + kLocalSlots : reinterpret_cast<uint32_t *>(agg_smem);  // fill counts of the item's fragments
     __shared__ unsigned long long s_item;
     __shared__ uint32_t s_next;                          // next fragment (or spill run) of the item to hand out
     __shared__ uint64_t s_spill_first[kMaxSources + 1];  // work-item index of each source's first spill slice
@@ -182,15 +186,17 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_kernel(const AggPara
         // (a straight-line "home buckets of all U first, probe loop for the rest" variant was
         // measured slower, 14.6 vs 9.4 ms per C2 step: the loop below already exits on its first
         // iteration nine times out of ten, and the variant loads every bucket twice on a miss)
-        uint32_t direct = live;
-        if (p.use_cache) {
-            direct = 0;
+        if constexpr (!kCache) {
+            const uint64_t one[U] = {1, 1, 1, 1};
+            if (live) created += table_add_many<U>(tv, h, one, live, full);
+            return;
+        }
+        uint32_t direct = 0;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (!((live >> u) & 1u)) continue;
-                const uint32_t bucket = (uint32_t)(((h[u] * kPhi) << p.part_bits) >> (64 - (kLocalBits - 2)));
-                if (h[u] == kEmpty || !local_count(lk, ld, h[u], bucket)) direct |= 1u << u;
-            }
+        for (int u = 0; u < U; ++u) {
+            if (!((live >> u) & 1u)) continue;
+            const uint32_t bucket = (uint32_t)(((h[u] * kPhi) << p.part_bits) >> (64 - (kLocalBits - 2)));
+            if (h[u] == kEmpty || !local_count(lk, ld, h[u], bucket)) direct |= 1u << u;
         }
         if (direct) {  // two at a time: four sets of bucket registers do not fit the register budget
             const uint64_t one[2] = {1, 1};
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_kernel(const AggPara
         __syncthreads();  // previous item fully merged; s_item free
         if (threadIdx.x == 0) { s_item = atomicAdd(p.work_counter, 1ULL); s_next = 0; }
         // empty the cache
-        if (p.use_cache) {
+        if (kCache) {
             for (uint32_t i = threadIdx.x; i < kLocalSlots / 2; i += kAggThreads)
                 reinterpret_cast<ulonglong2 *>(lk)[i] = make_ulonglong2(kEmpty, kEmpty);
             for (uint32_t i = threadIdx.x; i < kLocalSlots / 4; i += kAggThreads)
@@ -313,7 +319,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_kernel(const AggPara
 
         // merge: distinct keys of this item, in slot order of the table (the cache index is the
         // next-lower bits of the same product h * phi)
-        if (p.use_cache) {
+        if (kCache) {
             constexpr int M = 2;
             for (uint32_t base = 0; base < kLocalSlots; base += kAggThreads * M) {
                 uint64_t key[M], inc[M];

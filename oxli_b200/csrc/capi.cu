@@ -571,13 +571,30 @@ oxg_status launch_part_a(oxg_table *t, ConsumeParams p, const PartPlan &pl, uint
 
 // the aggregation kernel is built for three CTA sizes (one CTA per SM each); OXLI_B200_AGG_THREADS picks
 static const int g_agg_threads = [] { const int v = env_int("OXLI_B200_AGG_THREADS", kAggThreadsDefault); return v == 512 || v == 768 || v == 1024 ? v : kAggThreadsDefault; }();
-int agg_threads() { return g_agg_threads; }
-const void *agg_fn() {
-    return g_agg_threads == 512 ? (const void *)aggregate_kernel<512> : g_agg_threads == 1024 ? (const void *)aggregate_kernel<1024> : (const void *)aggregate_kernel<768>;
+// ... and OXLI_B200_AGG_THREADS_DIRECT for the variant without the cache, which is bound by the latency
+// of its table loads and wants every thread it can get (C3-shaped input, pass B per step:
+// 512 / 768 / 1024 threads = 46.2 / 35.3 / 32.4 ms)
+static const int g_agg_threads_direct = [] { const int v = env_int("OXLI_B200_AGG_THREADS_DIRECT", 1024); return v == 512 || v == 768 || v == 1024 ? v : 1024; }();
+int agg_threads(bool cache = true) { return cache ? g_agg_threads : g_agg_threads_direct; }
+const void *agg_fn(bool cache = true) {
+    if (!cache) return g_agg_threads_direct == 512 ? (const void *)aggregate_kernel<512, false> : g_agg_threads_direct == 768 ? (const void *)aggregate_kernel<768, false> : (const void *)aggregate_kernel<1024, false>;
+    return g_agg_threads == 512 ? (const void *)aggregate_kernel<512, true> : g_agg_threads == 1024 ? (const void *)aggregate_kernel<1024, true> : (const void *)aggregate_kernel<768, true>;
 }
-oxg_status launch_aggregate(const AggParams &a, int grid, size_t smem, cudaStream_t stream) {
+// grid: one CTA per SM and item at most (the cached kernel fills an SM's shared memory; the direct
+// one is held to one CTA per SM by its registers)
+oxg_status launch_aggregate(DeviceCtx *c, const AggParams &a, cudaStream_t stream) {
+    const bool cache = a.use_cache != 0;
+    const size_t smem = aggregate_smem_bytes(cache);
+    if (cache && !c->agg_attr_done) {
+        CU(cudaFuncSetAttribute(agg_fn(true), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->agg_attr_done = true;
+    }
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_fn(cache), agg_threads(cache), smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const uint64_t items = (uint64_t)a.n_parts * a.groups;
+    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(items, (uint64_t)c->sms * per_sm));
     void *args[] = {const_cast<AggParams *>(&a)};
-    CU(cudaLaunchKernel(agg_fn(), dim3(grid), dim3(g_agg_threads), args, smem, stream));
+    CU(cudaLaunchKernel(agg_fn(cache), dim3(grid), dim3(agg_threads(cache)), args, smem, stream));
     return OXG_OK;
 }
 
@@ -607,11 +624,6 @@ uint32_t aggregate_groups(const PartPlan &pl, uint32_t use_cache, uint64_t hashe
 // pass B over n_src sources (one, this device's own pass A output, without sharding)
 oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src, int n_src, uint64_t windows) {
     DeviceCtx *c = t->ctx;
-    const size_t smem = aggregate_smem_bytes();
-    if (!c->agg_attr_done) {
-        CU(cudaFuncSetAttribute(agg_fn(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        c->agg_attr_done = true;
-    }
     AggParams a{};
     a.table = view_of(t, true);
     for (int s = 0; s < n_src; ++s) a.src[s] = src[s];
@@ -622,11 +634,7 @@ oxg_status launch_part_b(oxg_table *t, const PartPlan &pl, const AggSource *src,
     a.work_counter = (unsigned long long *)&t->d_ctrl->absorb_counter;
     a.use_cache = use_cache_for(t, pl, windows);
     a.groups = aggregate_groups(pl, a.use_cache, windows);
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agg_fn(), agg_threads(), smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const uint64_t items = (uint64_t)pl.n_parts * a.groups;
-    const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(items, (uint64_t)c->sms * per_sm));
-    TRY(launch_aggregate(a, grid, smem, c->stream));
+    TRY(launch_aggregate(c, a, c->stream));
     LAUNCHED();
     CU(cudaGetLastError());
     return OXG_OK;
