@@ -21,6 +21,7 @@ exchange, barriers and the max over ranks); the product path is the C ABI.
 from __future__ import annotations
 
 import argparse
+import atexit
 import json
 import os
 import subprocess
@@ -109,6 +110,7 @@ class ClockSampler:
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            atexit.register(self.close)  # (a bench that dies before its timed region must not leave the poller behind)
         except Exception:
             self.proc = None
 
